@@ -1,0 +1,773 @@
+// capi.cu -- the extern "C" boundary (include/gymrs_b200.h) over kernels.cu.
+//
+// One gymrs_env owns: the f32 SoA state of num_envs independent env instances in HBM,
+// the per-step result arrays (reward / done / truncated), a CUDA stream, a pinned error
+// word the kernels raise on an invalid action, and the f64 parameter block the
+// reference keeps as `pub` fields.  There is deliberately no CPU path in this file:
+// without a device every entry point that needs one fails with GYMRS_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <random>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../include/gymrs_b200.h"
+#include "kernels.hpp"
+
+using namespace gymrs;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(GYMRS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(expr)                                                        \
+    do {                                                                \
+        cudaError_t e_ = (expr);                                        \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #expr);             \
+    } while (0)
+
+// largest float <= v  /  smallest float >= v: lets a float compare against a double
+// threshold be decided exactly ((x > T) == (x > f32_floor(T)) for every float x).
+float f32_floor(double v)
+{
+    float f = (float)v;
+    if ((double)f > v) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
+    return f;
+}
+float f32_ceil(double v)
+{
+    float f = (float)v;
+    if ((double)f < v) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+    return f;
+}
+
+void make_reset_box(ResetBox &rb, int dim, const float *low, const float *high)
+{
+    for (int i = 0; i < 4; ++i) {
+        rb.low[i] = 0.f; rb.scale[i] = 0.f; rb.cap[i] = 0.f;
+    }
+    for (int i = 0; i < dim; ++i) {
+        rb.low[i] = low[i];
+        rb.scale[i] = high[i] - low[i];
+        rb.cap[i] = high[i] > low[i] ? std::nextafterf(high[i], low[i]) : low[i];
+    }
+}
+
+} // namespace
+
+struct gymrs_env {
+    int kind = 0;
+    uint64_t n = 0, ld = 0, global_off = 0;
+    int device = 0;
+    uint32_t flags = 0;
+    uint32_t state_dim = 0, obs_dim = 0;
+
+    gymrs_cartpole_params cp{};
+    gymrs_mountain_car_params mc{};
+    gymrs_pendulum_params pd{};
+    CartPoleP dcp{};
+    MountainCarP dmc{};
+    PendulumP dpd{};
+    float reset_low[4] = {0, 0, 0, 0}, reset_high[4] = {0, 0, 0, 0};
+
+    float *state = nullptr, *obs = nullptr, *reward = nullptr;
+    uint8_t *done = nullptr, *truncated = nullptr;
+    int32_t *sbt = nullptr;
+    uint32_t *elapsed = nullptr;
+    void *d_actions = nullptr; // staging for *_host entry points
+    uint32_t *err_host = nullptr, *err_dev = nullptr;
+
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_streams[2] = {nullptr, nullptr};
+    cudaEvent_t ev[8] = {};
+
+    uint64_t seed = 0;       // Philox key of the auto-reset stream
+    uint64_t step_count = 0; // steps since the last full reset; epoch of an auto-reset = step_count + 1
+    bool sbt_dirty = false;  // some env may hold steps_beyond_terminated = Some(_)
+    int sticky = 0;
+    int vec = 0, block = 0, pdl = 1;
+};
+
+namespace {
+
+void default_reset_bounds(int kind, float *low, float *high)
+{
+    if (kind == GYMRS_CARTPOLE) { // cartpole.rs:353-361
+        for (int i = 0; i < 4; ++i) { low[i] = -0.05f; high[i] = 0.05f; }
+    } else if (kind == GYMRS_MOUNTAIN_CAR) { // mountain_car.rs:176-187
+        low[0] = -0.6f; high[0] = -0.4f; low[1] = 0.f; high[1] = 0.f;
+    } else {
+        low[0] = -3.14159274f; high[0] = 3.14159274f; low[1] = -1.f; high[1] = 1.f;
+    }
+}
+
+// Fold the f64 `pub` fields into the f32 block the kernels take by value.
+void fold_params(gymrs_env *e)
+{
+    if (e->kind == GYMRS_CARTPOLE) {
+        const gymrs_cartpole_params &p = e->cp;
+        const double total_mass = p.masspole + p.masscart;    // cartpole.rs:146-148
+        const double polemass_length = p.masspole + p.length; // cartpole.rs:150-152 (a SUM, sic)
+        CartPoleP &d = e->dcp;
+        d.tau = (float)p.tau;
+        d.force_over_m = (float)(p.force_mag / total_mass);
+        d.pml_over_m = (float)(polemass_length / total_mass);
+        d.gravity = (float)p.gravity;
+        d.den_a = (float)(p.length * (4.0 / 3.0));
+        d.den_b = (float)(p.length * p.masspole / total_mass);
+        d.x_thr = f32_floor(p.x_threshold);
+        d.th_thr = f32_floor(p.theta_threshold_radians);
+        d.semi_implicit = p.kinematics_integrator != 0;
+        make_reset_box(d.rb, 4, e->reset_low, e->reset_high);
+    } else if (e->kind == GYMRS_MOUNTAIN_CAR) {
+        const gymrs_mountain_car_params &p = e->mc;
+        MountainCarP &d = e->dmc;
+        d.force = (float)p.force;
+        d.neg_gravity = (float)(-p.gravity);
+        d.max_speed = (float)p.max_speed;
+        d.min_position = (float)p.min_position;
+        d.max_position = (float)p.max_position;
+        d.goal_position = f32_ceil(p.goal_position);
+        d.goal_velocity = f32_ceil(p.goal_velocity);
+        make_reset_box(d.rb, 1, e->reset_low, e->reset_high);
+    } else {
+        const gymrs_pendulum_params &p = e->pd;
+        PendulumP &d = e->dpd;
+        d.max_speed = (float)p.max_speed;
+        d.max_torque = (float)p.max_torque;
+        d.dt = (float)p.dt;
+        d.c_sin = (float)(3.0 * p.g / (2.0 * p.l));
+        d.c_u = (float)(3.0 / (p.m * p.l * p.l));
+        make_reset_box(d.rb, 2, e->reset_low, e->reset_high);
+    }
+}
+
+uint32_t max_episode_steps(const gymrs_env *e)
+{
+    int32_t m = e->kind == GYMRS_CARTPOLE ? e->cp.max_episode_steps
+              : e->kind == GYMRS_MOUNTAIN_CAR ? e->mc.max_episode_steps : e->pd.max_episode_steps;
+    return m > 0 ? (uint32_t)m : 0xFFFFFFFFu;
+}
+
+BatchArgs base_args(const gymrs_env *e)
+{
+    BatchArgs a = {};
+    a.state = e->state;
+    a.obs = (e->obs == e->state) ? nullptr : e->obs;
+    a.ld = e->ld;
+    a.reward = e->reward;
+    a.done = e->done;
+    a.truncated = e->truncated;
+    a.sbt = e->sbt;
+    a.elapsed = e->elapsed;
+    a.max_steps = max_episode_steps(e);
+    a.n = e->n;
+    a.global_off = e->global_off;
+    a.seed = e->seed;
+    a.epoch = e->step_count + 1;
+    a.err = e->err_dev;
+    return a;
+}
+
+// a view of envs [begin, begin + count) of the handle
+BatchArgs slice_args(const gymrs_env *e, uint64_t begin, uint64_t count)
+{
+    BatchArgs a = base_args(e);
+    a.state += begin;
+    if (a.obs) a.obs += begin;
+    a.reward += begin;
+    a.done += begin;
+    a.truncated += begin;
+    if (a.sbt) a.sbt += begin;
+    if (a.elapsed) a.elapsed += begin;
+    a.n = count;
+    a.global_off += begin;
+    return a;
+}
+
+LaunchOpts make_opts(const gymrs_env *e, uint32_t step_flags)
+{
+    LaunchOpts o = {};
+    o.autoreset = (step_flags & GYMRS_STEP_AUTORESET) != 0;
+    o.time_limit = (e->flags & GYMRS_FLAG_TIME_LIMIT) != 0;
+    // steps_beyond_terminated only matters once a terminated env has been stepped without a
+    // reset; with auto-reset from a clean state every env is None at every step.
+    o.use_sbt = e->kind == GYMRS_CARTPOLE && (!o.autoreset || e->sbt_dirty);
+    o.pdl = e->pdl;
+    o.vec = e->vec;
+    o.block = e->block;
+    return o;
+}
+
+cudaError_t do_step(gymrs_env *e, const BatchArgs &a, const LaunchOpts &o, cudaStream_t s, bool rollout)
+{
+    switch (e->kind) {
+    case GYMRS_CARTPOLE:
+        return rollout ? launch_rollout<CartPole>(e->dcp, a, o, s) : launch_step<CartPole>(e->dcp, a, o, s);
+    case GYMRS_MOUNTAIN_CAR:
+        return rollout ? launch_rollout<MountainCar>(e->dmc, a, o, s) : launch_step<MountainCar>(e->dmc, a, o, s);
+    default:
+        return rollout ? launch_rollout<Pendulum>(e->dpd, a, o, s) : launch_step<Pendulum>(e->dpd, a, o, s);
+    }
+}
+
+cudaError_t do_reset(gymrs_env *e, const BatchArgs &a, const uint8_t *mask, cudaStream_t s)
+{
+    switch (e->kind) {
+    case GYMRS_CARTPOLE: return launch_reset<CartPole>(e->dcp, a, mask, s);
+    case GYMRS_MOUNTAIN_CAR: return launch_reset<MountainCar>(e->dmc, a, mask, s);
+    default: return launch_reset<Pendulum>(e->dpd, a, mask, s);
+    }
+}
+
+uint64_t entropy64()
+{
+    std::random_device rd; // seeding.rs:22 thread_rng().gen()
+    return ((uint64_t)rd() << 32) ^ (uint64_t)rd();
+}
+
+void after_step(gymrs_env *e, uint32_t step_flags, uint32_t n_steps)
+{
+    e->step_count += n_steps;
+    if (e->kind == GYMRS_CARTPOLE && !(step_flags & GYMRS_STEP_AUTORESET)) e->sbt_dirty = true;
+}
+
+int free_env(gymrs_env *e)
+{
+    if (!e) return GYMRS_OK;
+    cudaSetDevice(e->device);
+    if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+    cudaFree(e->state);
+    if (e->obs && e->obs != e->state) cudaFree(e->obs);
+    cudaFree(e->reward);
+    cudaFree(e->done);
+    cudaFree(e->truncated);
+    cudaFree(e->sbt);
+    cudaFree(e->elapsed);
+    cudaFree(e->d_actions);
+    if (e->err_host) cudaFreeHost(e->err_host);
+    for (auto &s : e->copy_streams) if (s) cudaStreamDestroy(s);
+    for (auto &v : e->ev) if (v) cudaEventDestroy(v);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return GYMRS_OK;
+}
+
+int alloc_env(gymrs_env *e)
+{
+    const uint64_t n = e->n;
+    e->ld = (n + 127) / 128 * 128; // rows start 512-byte aligned
+    if (e->ld == 0) e->ld = 128;
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    for (auto &s : e->copy_streams) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto &v : e->ev) CU(cudaEventCreateWithFlags(&v, cudaEventDisableTiming));
+    CU(cudaMalloc(&e->state, sizeof(float) * e->state_dim * e->ld));
+    CU(cudaMemsetAsync(e->state, 0, sizeof(float) * e->state_dim * e->ld, e->stream));
+    if (e->kind == GYMRS_PENDULUM) {
+        CU(cudaMalloc(&e->obs, sizeof(float) * e->obs_dim * e->ld));
+        CU(cudaMemsetAsync(e->obs, 0, sizeof(float) * e->obs_dim * e->ld, e->stream));
+    } else {
+        e->obs = e->state;
+    }
+    CU(cudaMalloc(&e->reward, sizeof(float) * e->ld));
+    CU(cudaMalloc(&e->done, e->ld));
+    CU(cudaMalloc(&e->truncated, e->ld));
+    CU(cudaMemsetAsync(e->reward, 0, sizeof(float) * e->ld, e->stream));
+    CU(cudaMemsetAsync(e->done, 0, e->ld, e->stream));
+    CU(cudaMemsetAsync(e->truncated, 0, e->ld, e->stream));
+    if (e->kind == GYMRS_CARTPOLE) {
+        CU(cudaMalloc(&e->sbt, sizeof(int32_t) * e->ld));
+        CU(cudaMemsetAsync(e->sbt, 0xFF, sizeof(int32_t) * e->ld, e->stream)); // -1 = None
+    }
+    if (e->flags & GYMRS_FLAG_TIME_LIMIT) {
+        CU(cudaMalloc(&e->elapsed, sizeof(uint32_t) * e->ld));
+        CU(cudaMemsetAsync(e->elapsed, 0, sizeof(uint32_t) * e->ld, e->stream));
+    }
+    CU(cudaHostAlloc(&e->err_host, 4 * sizeof(uint32_t), cudaHostAllocMapped));
+    std::memset(e->err_host, 0, 4 * sizeof(uint32_t));
+    CU(cudaHostGetDevicePointer(&e->err_dev, e->err_host, 0));
+    return GYMRS_OK;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int gymrs_abi_version(void) { return GYMRS_ABI_VERSION; }
+
+const char *gymrs_last_error(void) { return g_last_error.c_str(); }
+
+int gymrs_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int gymrs_default_params(int kind, void *params)
+{
+    if (!params) return fail(GYMRS_ERR_BAD_ARG, "params is NULL");
+    if (kind == GYMRS_CARTPOLE) {
+        gymrs_cartpole_params p = {};
+        p.gravity = 9.8;                                       // cartpole.rs:94
+        p.masscart = 1.0;                                      // :95
+        p.masspole = 0.1;                                      // :96
+        p.length = 0.5;                                        // :97
+        p.force_mag = 10.0;                                    // :98
+        p.tau = 0.02;                                          // :99
+        p.kinematics_integrator = 0;                           // :100
+        p.theta_threshold_radians = 12. * 2. * 3.14159265358979323846 / 360.; // :102
+        p.x_threshold = 2.4;                                   // :103
+        p.max_episode_steps = 500;                             // doc :50
+        *(gymrs_cartpole_params *)params = p;
+    } else if (kind == GYMRS_MOUNTAIN_CAR) {
+        gymrs_mountain_car_params p = {};
+        p.min_position = -1.2;  // mountain_car.rs:344
+        p.max_position = 0.6;   // :345
+        p.max_speed = 0.07;     // :346
+        p.goal_position = 0.5;  // :347
+        p.goal_velocity = 0.;   // :348
+        p.force = 0.001;        // :350
+        p.gravity = 0.0025;     // :351
+        p.max_episode_steps = 200; // doc :45
+        *(gymrs_mountain_car_params *)params = p;
+    } else if (kind == GYMRS_PENDULUM) {
+        gymrs_pendulum_params p = {};
+        p.max_speed = 8.0; p.max_torque = 2.0; p.dt = 0.05; p.g = 10.0; p.m = 1.0; p.l = 1.0;
+        p.max_episode_steps = 200;
+        *(gymrs_pendulum_params *)params = p;
+    } else {
+        return fail(GYMRS_ERR_BAD_ARG, "unknown env kind");
+    }
+    return GYMRS_OK;
+}
+
+int gymrs_create(int kind, uint64_t num_envs, int device, uint64_t global_env_offset,
+                 const void *params, uint32_t flags, gymrs_env **out)
+{
+    if (!out) return fail(GYMRS_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    if (kind < GYMRS_CARTPOLE || kind > GYMRS_PENDULUM) return fail(GYMRS_ERR_BAD_ARG, "unknown env kind");
+    if (num_envs == 0) return fail(GYMRS_ERR_BAD_ARG, "num_envs must be > 0");
+    if (num_envs > (1ull << 40)) return fail(GYMRS_ERR_BAD_ARG, "num_envs too large");
+    int ndev = gymrs_device_count();
+    if (ndev <= 0) return fail(GYMRS_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(GYMRS_ERR_BAD_ARG, "device ordinal out of range");
+
+    gymrs_env *e = new (std::nothrow) gymrs_env();
+    if (!e) return fail(GYMRS_ERR_ALLOC, "host allocation failed");
+    e->kind = kind;
+    e->n = num_envs;
+    e->device = device;
+    e->global_off = global_env_offset;
+    e->flags = flags;
+    e->state_dim = kind == GYMRS_CARTPOLE ? 4 : 2;
+    e->obs_dim = kind == GYMRS_CARTPOLE ? 4 : (kind == GYMRS_MOUNTAIN_CAR ? 2 : 3);
+    gymrs_default_params(kind, kind == GYMRS_CARTPOLE ? (void *)&e->cp
+                               : kind == GYMRS_MOUNTAIN_CAR ? (void *)&e->mc : (void *)&e->pd);
+    if (params) {
+        if (kind == GYMRS_CARTPOLE) e->cp = *(const gymrs_cartpole_params *)params;
+        else if (kind == GYMRS_MOUNTAIN_CAR) e->mc = *(const gymrs_mountain_car_params *)params;
+        else e->pd = *(const gymrs_pendulum_params *)params;
+    }
+    default_reset_bounds(kind, e->reset_low, e->reset_high);
+    fold_params(e);
+    int rc = alloc_env(e);
+    if (rc != GYMRS_OK) {
+        std::string msg = g_last_error;
+        free_env(e);
+        return fail(rc, msg);
+    }
+    // ::new samples an initial state from an entropy-seeded RNG (cartpole.rs:92,120)
+    rc = gymrs_reset(e, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc != GYMRS_OK) {
+        std::string msg = g_last_error;
+        free_env(e);
+        return fail(rc, msg);
+    }
+    *out = e;
+    return GYMRS_OK;
+}
+
+int gymrs_destroy(gymrs_env *env) { return free_env(env); }
+
+int gymrs_clone(const gymrs_env *src, gymrs_env **out)
+{
+    if (!src || !out) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    *out = nullptr;
+    gymrs_env *e = new (std::nothrow) gymrs_env();
+    if (!e) return fail(GYMRS_ERR_ALLOC, "host allocation failed");
+    e->kind = src->kind; e->n = src->n; e->device = src->device; e->global_off = src->global_off;
+    e->flags = src->flags; e->state_dim = src->state_dim; e->obs_dim = src->obs_dim;
+    e->cp = src->cp; e->mc = src->mc; e->pd = src->pd;
+    e->dcp = src->dcp; e->dmc = src->dmc; e->dpd = src->dpd;
+    std::memcpy(e->reset_low, src->reset_low, sizeof e->reset_low);
+    std::memcpy(e->reset_high, src->reset_high, sizeof e->reset_high);
+    e->seed = src->seed; e->step_count = src->step_count; e->sbt_dirty = src->sbt_dirty;
+    e->vec = src->vec; e->block = src->block; e->pdl = src->pdl;
+    int rc = alloc_env(e);
+    if (rc != GYMRS_OK) {
+        std::string msg = g_last_error;
+        free_env(e);
+        return fail(rc, msg);
+    }
+    // order the copies after everything already queued on the source's stream
+    cudaError_t ce = cudaStreamSynchronize(src->stream);
+    auto cp = [&](void *d, const void *s, size_t b) {
+        if (ce == cudaSuccess && d && s) ce = cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, e->stream);
+    };
+    cp(e->state, src->state, sizeof(float) * e->state_dim * e->ld);
+    if (e->obs != e->state) cp(e->obs, src->obs, sizeof(float) * e->obs_dim * e->ld);
+    cp(e->reward, src->reward, sizeof(float) * e->ld);
+    cp(e->done, src->done, e->ld);
+    cp(e->truncated, src->truncated, e->ld);
+    cp(e->sbt, src->sbt, sizeof(int32_t) * e->ld);
+    cp(e->elapsed, src->elapsed, sizeof(uint32_t) * e->ld);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) {
+        free_env(e);
+        return cuda_fail(ce, "gymrs_clone");
+    }
+    *out = e;
+    return GYMRS_OK;
+}
+
+int gymrs_set_params(gymrs_env *e, const void *params)
+{
+    if (!e || !params) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    if (e->kind == GYMRS_CARTPOLE) e->cp = *(const gymrs_cartpole_params *)params;
+    else if (e->kind == GYMRS_MOUNTAIN_CAR) e->mc = *(const gymrs_mountain_car_params *)params;
+    else e->pd = *(const gymrs_pendulum_params *)params;
+    fold_params(e);
+    return GYMRS_OK;
+}
+
+int gymrs_get_params(const gymrs_env *e, void *params)
+{
+    if (!e || !params) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    if (e->kind == GYMRS_CARTPOLE) *(gymrs_cartpole_params *)params = e->cp;
+    else if (e->kind == GYMRS_MOUNTAIN_CAR) *(gymrs_mountain_car_params *)params = e->mc;
+    else *(gymrs_pendulum_params *)params = e->pd;
+    return GYMRS_OK;
+}
+
+int gymrs_set_stream(gymrs_env *e, void *cuda_stream)
+{
+    if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return GYMRS_OK;
+}
+
+int gymrs_get_stream(const gymrs_env *e, void **cuda_stream)
+{
+    if (!e || !cuda_stream) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    *cuda_stream = (void *)e->stream;
+    return GYMRS_OK;
+}
+
+// Tuning knobs (not part of the reference surface); see the header for the pdl contract.
+int gymrs_set_launch_config(gymrs_env *e, int vec, int block, int pdl)
+{
+    if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
+    if (!(vec == 0 || vec == 1 || vec == 2 || vec == 4)) return fail(GYMRS_ERR_BAD_ARG, "vec must be 0, 1, 2 or 4");
+    if (block != 0 && (block < 32 || block > 256 || block % 32)) return fail(GYMRS_ERR_BAD_ARG, "block must be a multiple of 32 in [32, 256]");
+    if (pdl < 0 || pdl > 2) return fail(GYMRS_ERR_BAD_ARG, "pdl must be 0, 1 or 2");
+    e->vec = vec; e->block = block; e->pdl = pdl;
+    return GYMRS_OK;
+}
+
+int gymrs_reset(gymrs_env *e, const uint64_t *seed, const float *low, const float *high,
+                const uint8_t *mask, uint64_t *seed_used)
+{
+    if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
+    if ((low == nullptr) != (high == nullptr)) return fail(GYMRS_ERR_BAD_ARG, "low and high must be given together");
+    CU(cudaSetDevice(e->device));
+    const uint64_t s = seed ? *seed : entropy64(); // seeding.rs:22
+    if (seed_used) *seed_used = s;
+    // `options: Option<BoxR<Obs>>` applies to this call only (cartpole.rs:351-365)
+    float lo[4], hi[4];
+    default_reset_bounds(e->kind, lo, hi);
+    if (low) {
+        for (uint32_t i = 0; i < e->state_dim; ++i) {
+            if (!(low[i] <= high[i])) return fail(GYMRS_ERR_BAD_ARG, "reset bounds need low <= high");
+            lo[i] = low[i]; hi[i] = high[i];
+        }
+    }
+    float keep_lo[4], keep_hi[4];
+    std::memcpy(keep_lo, e->reset_low, sizeof keep_lo);
+    std::memcpy(keep_hi, e->reset_high, sizeof keep_hi);
+    std::memcpy(e->reset_low, lo, sizeof lo);
+    std::memcpy(e->reset_high, hi, sizeof hi);
+    fold_params(e);
+    BatchArgs a = base_args(e);
+    a.seed = s;
+    cudaError_t ce = do_reset(e, a, mask, e->stream);
+    std::memcpy(e->reset_low, keep_lo, sizeof keep_lo);
+    std::memcpy(e->reset_high, keep_hi, sizeof keep_hi);
+    fold_params(e);
+    if (ce != cudaSuccess) return cuda_fail(ce, "reset launch");
+    if (!mask) { // a full reset restarts the handle's auto-reset stream
+        e->seed = s;
+        e->step_count = 0;
+        e->sbt_dirty = false;
+    }
+    return GYMRS_OK;
+}
+
+int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
+{
+    if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(e->device));
+    BatchArgs a = base_args(e);
+    a.actions = actions;
+    CU(do_step(e, a, make_opts(e, step_flags), e->stream, false));
+    after_step(e, step_flags, 1);
+    return GYMRS_OK;
+}
+
+int gymrs_step_host(gymrs_env *e, const void *actions, uint32_t step_flags,
+                    float *obs, float *reward, uint8_t *done, uint8_t *truncated)
+{
+    if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(e->device));
+    if (!e->d_actions) CU(cudaMalloc(&e->d_actions, 4 * e->ld));
+    // Chunked three-stage pipeline: H2D(actions) -> step -> D2H(results), chunk c+1's copy-in
+    // and chunk c-1's copy-out overlap chunk c's kernel.  Chunk boundaries are multiples of
+    // 1024 envs so every chunk keeps the 128-bit access path.
+    const uint64_t n = e->n;
+    uint64_t nchunk = n >= (1u << 18) ? 4 : 1;
+    uint64_t per = ((n + nchunk - 1) / nchunk + 1023) / 1024 * 1024;
+    cudaStream_t h2d = e->copy_streams[0], d2h = e->copy_streams[1], cs = e->stream;
+    LaunchOpts o = make_opts(e, step_flags);
+    o.pdl = 0;
+    // everything queued earlier on the compute stream (reset, set_state) precedes the copies
+    CU(cudaEventRecord(e->ev[7], cs));
+    CU(cudaStreamWaitEvent(h2d, e->ev[7], 0));
+    CU(cudaStreamWaitEvent(d2h, e->ev[7], 0));
+    int c = 0;
+    for (uint64_t b = 0; b < n; b += per, ++c) {
+        const uint64_t cnt = (b + per <= n) ? per : n - b;
+        cudaEvent_t in_ready = e->ev[c % 3], out_ready = e->ev[3 + c % 3];
+        CU(cudaMemcpyAsync((char *)e->d_actions + 4 * b, (const char *)actions + 4 * b, 4 * cnt,
+                           cudaMemcpyHostToDevice, h2d));
+        CU(cudaEventRecord(in_ready, h2d));
+        CU(cudaStreamWaitEvent(cs, in_ready, 0));
+        BatchArgs a = slice_args(e, b, cnt);
+        a.actions = (const char *)e->d_actions + 4 * b;
+        CU(do_step(e, a, o, cs, false));
+        CU(cudaEventRecord(out_ready, cs));
+        CU(cudaStreamWaitEvent(d2h, out_ready, 0));
+        if (obs)
+            CU(cudaMemcpy2DAsync(obs + b, sizeof(float) * n, e->obs + b, sizeof(float) * e->ld,
+                                 sizeof(float) * cnt, e->obs_dim, cudaMemcpyDeviceToHost, d2h));
+        if (reward) CU(cudaMemcpyAsync(reward + b, e->reward + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, d2h));
+        if (done) CU(cudaMemcpyAsync(done + b, e->done + b, cnt, cudaMemcpyDeviceToHost, d2h));
+        if (truncated) CU(cudaMemcpyAsync(truncated + b, e->truncated + b, cnt, cudaMemcpyDeviceToHost, d2h));
+    }
+    after_step(e, step_flags, 1);
+    CU(cudaStreamSynchronize(d2h));
+    CU(cudaStreamSynchronize(cs));
+    return GYMRS_OK;
+}
+
+int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t step_flags,
+                  float *obs_out, float *reward_out, uint8_t *done_out)
+{
+    if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    if (n_steps == 0) return GYMRS_OK;
+    CU(cudaSetDevice(e->device));
+    BatchArgs a = base_args(e);
+    a.actions = actions;
+    a.n_steps = n_steps;
+    a.act_ld = e->n;
+    a.out_ld = e->n;
+    a.obs_out = obs_out;
+    a.reward_out = reward_out;
+    a.done_out = done_out;
+    CU(do_step(e, a, make_opts(e, step_flags), e->stream, true));
+    after_step(e, step_flags, n_steps);
+    return GYMRS_OK;
+}
+
+int gymrs_get_state(gymrs_env *e, float *state, int32_t *sbt)
+{
+    if (!e || !state) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpy2DAsync(state, sizeof(float) * e->n, e->state, sizeof(float) * e->ld,
+                         sizeof(float) * e->n, e->state_dim, cudaMemcpyDeviceToHost, e->stream));
+    if (sbt) {
+        if (!e->sbt) return fail(GYMRS_ERR_UNSUPPORTED, "steps_beyond_terminated exists for CartPole only");
+        CU(cudaMemcpyAsync(sbt, e->sbt, sizeof(int32_t) * e->n, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    return GYMRS_OK;
+}
+
+int gymrs_set_state(gymrs_env *e, const float *state, const int32_t *sbt)
+{
+    if (!e || !state) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpy2DAsync(e->state, sizeof(float) * e->ld, state, sizeof(float) * e->n,
+                         sizeof(float) * e->n, e->state_dim, cudaMemcpyHostToDevice, e->stream));
+    if (e->sbt) {
+        if (sbt) {
+            CU(cudaMemcpyAsync(e->sbt, sbt, sizeof(int32_t) * e->n, cudaMemcpyHostToDevice, e->stream));
+            e->sbt_dirty = true;
+        } else {
+            CU(cudaMemsetAsync(e->sbt, 0xFF, sizeof(int32_t) * e->ld, e->stream));
+            e->sbt_dirty = false;
+        }
+    } else if (sbt) {
+        return fail(GYMRS_ERR_UNSUPPORTED, "steps_beyond_terminated exists for CartPole only");
+    }
+    if (e->elapsed) CU(cudaMemsetAsync(e->elapsed, 0, sizeof(uint32_t) * e->ld, e->stream));
+    if (e->kind == GYMRS_PENDULUM) CU(launch_pendulum_obs(base_args(e), e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return GYMRS_OK;
+}
+
+int gymrs_get_buffers(gymrs_env *e, gymrs_buffers *out)
+{
+    if (!e || !out) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    out->num_envs = e->n;
+    out->ld = e->ld;
+    out->state_dim = e->state_dim;
+    out->obs_dim = e->obs_dim;
+    out->state = e->state;
+    out->obs = e->obs;
+    out->reward = e->reward;
+    out->done = e->done;
+    out->truncated = e->truncated;
+    out->steps_beyond_terminated = e->sbt;
+    out->elapsed_steps = e->elapsed;
+    return GYMRS_OK;
+}
+
+int gymrs_action_space(const gymrs_env *e, uint64_t *n, float *low, float *high)
+{
+    if (!e || !n) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    if (e->kind == GYMRS_CARTPOLE) *n = 2;          // Discrete(2), cartpole.rs:112
+    else if (e->kind == GYMRS_MOUNTAIN_CAR) *n = 3; // Discrete(3), mountain_car.rs:363
+    else {
+        *n = 0;
+        if (low) *low = (float)-e->pd.max_torque;
+        if (high) *high = (float)e->pd.max_torque;
+    }
+    return GYMRS_OK;
+}
+
+int gymrs_observation_space(const gymrs_env *e, double *low, double *high)
+{
+    if (!e || !low || !high) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    const double inf = std::numeric_limits<double>::infinity();
+    if (e->kind == GYMRS_CARTPOLE) { // cartpole.rs:105-113
+        high[0] = e->cp.x_threshold * 2.;
+        high[1] = inf;
+        high[2] = e->cp.theta_threshold_radians * 2.;
+        high[3] = inf;
+        for (int i = 0; i < 4; ++i) low[i] = -high[i];
+    } else if (e->kind == GYMRS_MOUNTAIN_CAR) { // mountain_car.rs:353-354
+        low[0] = e->mc.min_position; low[1] = -e->mc.max_speed;
+        high[0] = e->mc.max_position; high[1] = e->mc.max_speed;
+    } else {
+        high[0] = 1.; high[1] = 1.; high[2] = e->pd.max_speed;
+        for (int i = 0; i < 3; ++i) low[i] = -high[i];
+    }
+    return GYMRS_OK;
+}
+
+int gymrs_reward_range(const gymrs_env *e, double *low, double *high)
+{
+    if (!e || !low || !high) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    *low = -std::numeric_limits<double>::infinity(); // core.rs:16-19
+    *high = std::numeric_limits<double>::infinity();
+    return GYMRS_OK;
+}
+
+int gymrs_num_envs(const gymrs_env *e, uint64_t *n)
+{
+    if (!e || !n) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    *n = e->n;
+    return GYMRS_OK;
+}
+
+int gymrs_kind_of(const gymrs_env *e, int *kind)
+{
+    if (!e || !kind) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    *kind = e->kind;
+    return GYMRS_OK;
+}
+
+int gymrs_sync(gymrs_env *e, uint64_t *bad_env)
+{
+    if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->err_host[0]) {
+        const uint64_t gid = (uint64_t)e->err_host[1] | ((uint64_t)e->err_host[2] << 32);
+        if (bad_env) *bad_env = gid;
+        e->err_host[0] = 0;
+        char buf[96];
+        // the reference's panic text: "{} usize invalid" (cartpole.rs:404) /
+        // "{} (usize) invalid" (mountain_car.rs:404); the action value itself stays on the device
+        std::snprintf(buf, sizeof buf, "invalid action for env %llu", (unsigned long long)gid);
+        return fail(GYMRS_ERR_INVALID_ACTION, buf);
+    }
+    return GYMRS_OK;
+}
+
+int gymrs_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(GYMRS_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    if (gymrs_device_count() <= 0) return fail(GYMRS_ERR_NO_DEVICE, "no CUDA device visible");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return GYMRS_OK;
+}
+
+int gymrs_host_free(void *p)
+{
+    if (!p) return GYMRS_OK;
+    CU(cudaFreeHost(p));
+    return GYMRS_OK;
+}
+
+// utils/custom/util_fns.rs:2-10
+double gymrs_clip(double value, double left_bound, double right_bound)
+{
+    if (left_bound <= value && value <= right_bound) return value;
+    else if (value > right_bound) return right_bound;
+    else return left_bound;
+}
+
+// spaces/discrete.rs:14-20
+int gymrs_discrete_contains(uint64_t n, uint64_t value) { return value < n; }
+
+// utils/seeding.rs:21-26
+uint64_t gymrs_rand_random(const uint64_t *seed) { return seed ? *seed : entropy64(); }
+
+} // extern "C"

@@ -1,0 +1,209 @@
+/*
+ * gymrs_b200.h -- C ABI of the B200-native batched classic-control env stepper.
+ *
+ * This is the drop-in boundary under gym-rs's `Env` / `EnvProperties` traits
+ * (reference: src/core.rs:25-57 and :60-90).  The reference has no FFI of its
+ * own -- its step path is a scalar Rust method on one env object -- so each
+ * entry point below names the Rust item it replaces.  One handle = one batch
+ * of independent env instances living in HBM on one GPU, f32 struct-of-arrays.
+ *
+ * Conventions
+ *   - every function returns a gymrs_status (0 = ok); nothing unwinds or aborts.
+ *     gymrs_last_error() gives a thread-local message for the last failure.
+ *   - a handle is NOT thread-safe (the reference's step/reset take &mut self,
+ *     core.rs:42,45).  Different handles may be driven from different threads.
+ *   - device work is enqueued on the handle's CUDA stream and is asynchronous
+ *     to the host unless a function says it synchronises.
+ *   - "device pointer" arguments must be readable from the handle's device;
+ *     "host pointer" arguments are plain memory (pinned memory from
+ *     gymrs_host_alloc makes the copies asynchronous and full speed).
+ *   - SoA layout: a [rows][num_envs] array is `rows` contiguous runs of
+ *     num_envs elements; handle-owned arrays use a row stride `ld` >= num_envs
+ *     (see gymrs_buffers).
+ *   - no CPU fallback exists: without a CUDA device gymrs_create fails with
+ *     GYMRS_ERR_NO_DEVICE.
+ */
+#ifndef GYMRS_B200_H
+#define GYMRS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GYMRS_ABI_VERSION 1
+
+typedef struct gymrs_env gymrs_env; /* opaque handle */
+
+typedef enum gymrs_kind {
+    GYMRS_CARTPOLE = 0,     /* src/envs/classical_control/cartpole.rs     */
+    GYMRS_MOUNTAIN_CAR = 1, /* src/envs/classical_control/mountain_car.rs */
+    GYMRS_PENDULUM = 2      /* not in the reference; upstream Gym Pendulum-v1 */
+} gymrs_kind;
+
+typedef enum gymrs_status {
+    GYMRS_OK = 0,
+    GYMRS_ERR_INVALID_ACTION = 1, /* reference: assert! panic, cartpole.rs:402-406, mountain_car.rs:402-406 */
+    GYMRS_ERR_BAD_ARG = 2,
+    GYMRS_ERR_CUDA = 3,
+    GYMRS_ERR_NO_DEVICE = 4,
+    GYMRS_ERR_ALLOC = 5,
+    GYMRS_ERR_UNSUPPORTED = 6
+} gymrs_status;
+
+/* gymrs_create flags */
+#define GYMRS_FLAG_TIME_LIMIT 0x1u /* keep a per-env step counter and raise `truncated`
+                                      at max_episode_steps.  OFF by default: the reference
+                                      documents truncation (cartpole.rs:50, mountain_car.rs:45)
+                                      but never implements it (truncated: false, cartpole.rs:480,
+                                      mountain_car.rs:432). */
+
+/* step flags */
+#define GYMRS_STEP_AUTORESET 0x1u  /* envs whose step ended the episode are re-sampled in the
+                                      same launch (what examples/cartpole.rs:23-28 does by hand);
+                                      the observation returned for them is the fresh one. */
+
+/* ---- physics parameters (the reference's `pub` fields; f64 like the reference,
+ *      rounded to f32 once on the host when the handle is created/updated) ---- */
+
+typedef struct gymrs_cartpole_params { /* cartpole.rs:63-80, defaults :94-103 */
+    double gravity, masscart, masspole, length, force_mag, tau;
+    double theta_threshold_radians, x_threshold;
+    int32_t kinematics_integrator; /* 0 Euler (default), 1 semi-implicit (:380-387) */
+    int32_t max_episode_steps;     /* used only with GYMRS_FLAG_TIME_LIMIT; default 500 */
+} gymrs_cartpole_params;
+
+typedef struct gymrs_mountain_car_params { /* mountain_car.rs:49-63, defaults :344-351 */
+    double min_position, max_position, max_speed, goal_position, goal_velocity;
+    double force, gravity;
+    int32_t max_episode_steps; /* default 200 */
+    int32_t _pad;
+} gymrs_mountain_car_params;
+
+typedef struct gymrs_pendulum_params { /* upstream Gym pendulum.py */
+    double max_speed, max_torque, dt, g, m, l;
+    int32_t max_episode_steps; /* default 200 */
+    int32_t _pad;
+} gymrs_pendulum_params;
+
+/* Device pointers into the handle's SoA arrays (valid until gymrs_destroy). */
+typedef struct gymrs_buffers {
+    uint64_t num_envs;
+    uint64_t ld;         /* row stride, in elements, of state/obs */
+    uint32_t state_dim;  /* CartPole 4 (x, x_dot, theta, theta_dot); MountainCar 2 (position, velocity);
+                            Pendulum 2 (theta, theta_dot) */
+    uint32_t obs_dim;    /* CartPole 4, MountainCar 2 (observation == state), Pendulum 3 (cos, sin, theta_dot) */
+    float *state;        /* [state_dim][ld] */
+    float *obs;          /* [obs_dim][ld]; same pointer as state when observation == state */
+    float *reward;       /* [num_envs]  ActionReward.reward   (core.rs:99) */
+    uint8_t *done;       /* [num_envs]  ActionReward.done     (core.rs:101) */
+    uint8_t *truncated;  /* [num_envs]  ActionReward.truncated(core.rs:103); all zero without TIME_LIMIT */
+    int32_t *steps_beyond_terminated; /* CartPole only: -1 = None, k = Some(k) (cartpole.rs:81); else NULL */
+    uint32_t *elapsed_steps;          /* TIME_LIMIT only, else NULL */
+} gymrs_buffers;
+
+/* ---- library ---- */
+int gymrs_abi_version(void);
+const char *gymrs_last_error(void);
+/* number of CUDA devices visible (0 when there is no driver/GPU) */
+int gymrs_device_count(void);
+
+/* Fills *params (a gymrs_*_params matching `kind`) with the reference defaults
+ * (cartpole.rs:94-103, mountain_car.rs:344-351). */
+int gymrs_default_params(int kind, void *params);
+
+/* ---- lifetime: CartPoleEnv::new / MountainCarEnv::new (cartpole.rs:91-144,
+ *      mountain_car.rs:341-389), Clone (core.rs:25), Drop ---- */
+/* global_env_offset: id of this handle's env 0 in the whole (possibly multi-GPU) batch;
+ * reset sampling is keyed by the global id, so results do not depend on sharding.
+ * params: NULL = defaults.  Like ::new, the initial state is an entropy-seeded reset. */
+int gymrs_create(int kind, uint64_t num_envs, int device, uint64_t global_env_offset,
+                 const void *params, uint32_t flags, gymrs_env **out);
+int gymrs_destroy(gymrs_env *env);
+int gymrs_clone(const gymrs_env *env, gymrs_env **out);
+
+/* The reference's physics constants are `pub` fields a caller may mutate between steps. */
+int gymrs_set_params(gymrs_env *env, const void *params);
+int gymrs_get_params(const gymrs_env *env, void *params);
+
+/* Run the handle's work on a caller-owned cudaStream_t (NULL restores the handle's own). */
+int gymrs_set_stream(gymrs_env *env, void *cuda_stream);
+int gymrs_get_stream(const gymrs_env *env, void **cuda_stream);
+
+/* ---- Env::reset (core.rs:45-50; cartpole.rs:485-516, mountain_car.rs:464-501) ----
+ * seed NULL = draw 64 bits of OS entropy (seeding.rs:22).  *seed_used (optional) receives
+ * the seed, mirroring rand_random's returned tuple (seeding.rs:21-26).
+ * low/high: host pointers to state_dim floats, or NULL for the reference defaults
+ * (`options: Option<BoxR<Obs>>`).  mask: device pointer to num_envs bytes, NULL = all envs.
+ * Env i takes its values from Philox4x32-10(key = seed, counter = (global id, epoch 0)). */
+int gymrs_reset(gymrs_env *env, const uint64_t *seed, const float *low, const float *high,
+                const uint8_t *mask, uint64_t *seed_used);
+
+/* ---- Env::step (core.rs:42; cartpole.rs:398-483, mountain_car.rs:398-435) ----
+ * actions: device pointer, int32[num_envs] for CartPole / MountainCar (Action = usize,
+ * cartpole.rs:390, mountain_car.rs:393), float[num_envs] for Pendulum.
+ * Results land in the handle's buffers (gymrs_buffers).  An action outside the action
+ * space leaves that env untouched and raises a sticky GYMRS_ERR_INVALID_ACTION that the
+ * next gymrs_sync reports (the reference panics). */
+int gymrs_step(gymrs_env *env, const void *actions, uint32_t step_flags);
+
+/* Same step with HOST buffers: copies actions in, steps, copies observation / reward / done
+ * out (any output pointer may be NULL to skip it) and synchronises.  obs: [obs_dim][num_envs]. */
+int gymrs_step_host(gymrs_env *env, const void *actions, uint32_t step_flags,
+                    float *obs, float *reward, uint8_t *done, uint8_t *truncated);
+
+/* Fused rollout: n_steps consecutive steps in ONE launch, state held in registers.
+ * actions: device [n_steps][num_envs].  Per-step results are streamed to the caller's
+ * device arrays (any may be NULL): obs_out [n_steps][obs_dim][num_envs],
+ * reward_out / done_out [n_steps][num_envs].  The handle's own buffers hold the last step. */
+int gymrs_rollout(gymrs_env *env, const void *actions, uint32_t n_steps, uint32_t step_flags,
+                  float *obs_out, float *reward_out, uint8_t *done_out);
+
+/* ---- state access: `pub state` (cartpole.rs:60, mountain_car.rs:74), Serialize/Clone ----
+ * host [state_dim][num_envs] floats; both synchronise.  sbt (CartPole, may be NULL):
+ * int32[num_envs], -1 = None. */
+int gymrs_get_state(gymrs_env *env, float *state, int32_t *sbt);
+int gymrs_set_state(gymrs_env *env, const float *state, const int32_t *sbt);
+int gymrs_get_buffers(gymrs_env *env, gymrs_buffers *out);
+
+/* ---- EnvProperties (core.rs:60-90) ---- */
+/* Discrete(n): *n = 2 / 3, low/high untouched.  Box (Pendulum): *n = 0, low/high = -+max_torque. */
+int gymrs_action_space(const gymrs_env *env, uint64_t *n, float *low, float *high);
+/* low/high: obs_dim doubles each (cartpole.rs:105-113, mountain_car.rs:353-364) */
+int gymrs_observation_space(const gymrs_env *env, double *low, double *high);
+/* (-inf, +inf), core.rs:16-19,81-83 */
+int gymrs_reward_range(const gymrs_env *env, double *low, double *high);
+int gymrs_num_envs(const gymrs_env *env, uint64_t *n);
+int gymrs_kind_of(const gymrs_env *env, int *kind);
+
+/* Wait for the handle's stream; returns the sticky error (invalid action / CUDA) and clears it.
+ * *bad_env (optional) receives the global id of one offending env. */
+int gymrs_sync(gymrs_env *env, uint64_t *bad_env);
+
+/* Launch tuning (not part of the reference surface).
+ * vec: env instances per thread, 0 = widest the buffer alignment allows (4), or 1 / 2 / 4.
+ * block: threads per CTA, 0 = 256.
+ * pdl: 0 = plain stream order; 1 (default) = programmatic dependent launch, the next step's
+ *      CTAs are scheduled while the previous step drains but touch memory only after it has
+ *      completed; 2 = as 1 and the action batch is read BEFORE that wait -- only valid when
+ *      the action buffer was complete before the previous launch in the stream started
+ *      (pre-generated rollouts), never when a policy kernel writes it just before the step. */
+int gymrs_set_launch_config(gymrs_env *env, int vec, int block, int pdl);
+
+/* Pinned host memory for the *_host entry points. */
+int gymrs_host_alloc(size_t bytes, void **out);
+int gymrs_host_free(void *p);
+
+/* Shared helpers restating small reference functions so bindings need no second copy:
+ * clip = utils/custom/util_fns.rs:2-10, contains = spaces/discrete.rs:14-20,
+ * rand_random = utils/seeding.rs:21-26 (returns the seed used). */
+double gymrs_clip(double value, double left_bound, double right_bound);
+int gymrs_discrete_contains(uint64_t n, uint64_t value);
+uint64_t gymrs_rand_random(const uint64_t *seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GYMRS_B200_H */

@@ -1,0 +1,148 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads, exports every symbol
+include/gymrs_b200.h declares, refuses to run without a device (no CPU fallback), and never
+touches the oracle.  Also the reference's own unit tests restated at the C-ABI level
+(src/utils/custom/util_fns.rs:16-32, src/spaces/discrete.rs:27-41, src/utils/seeding.rs:33-39).
+No compute entry point is called here.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "gymrs_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gymrs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from gym_rs_b200 import _capi
+    L = _capi.load()
+    out = subprocess.run(["nm", "-D", "--defined-only", _capi.lib_path()], capture_output=True,
+                         text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (gymrs_[a-z0-9_]+)", out))
+    declared = header_functions()
+    assert len(declared) >= 28
+    for name in declared:
+        assert name in exported, f"{name} declared in the header but not exported"
+        assert hasattr(L, name)
+    # the ctypes table and the header agree exactly
+    assert sorted(_capi.SIGNATURES) == declared
+    assert L.gymrs_abi_version() == 1
+
+
+def test_library_is_compiled_for_sm_100a():
+    from gym_rs_b200 import _capi
+    _capi.load()
+    out = subprocess.run(["cuobjdump", "-lelf", _capi.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_struct_sizes_match_the_header():
+    from gym_rs_b200 import _capi
+    assert C.sizeof(_capi.CartPoleParams) == 8 * 8 + 8
+    assert C.sizeof(_capi.MountainCarParams) == 7 * 8 + 8
+    assert C.sizeof(_capi.PendulumParams) == 6 * 8 + 8
+    assert C.sizeof(_capi.Buffers) == 16 + 8 + 7 * 8
+
+
+def test_default_params_are_the_reference_constants():
+    from gym_rs_b200 import _capi
+    L = _capi.load()
+    p = _capi.CartPoleParams()
+    assert L.gymrs_default_params(_capi.CARTPOLE, C.byref(p)) == 0
+    assert (p.gravity, p.masscart, p.masspole, p.length, p.force_mag, p.tau) == (9.8, 1.0, 0.1, 0.5, 10.0, 0.02)
+    assert p.theta_threshold_radians == 0.20943951023931953 and p.x_threshold == 2.4
+    assert p.kinematics_integrator == 0 and p.max_episode_steps == 500
+    m = _capi.MountainCarParams()
+    assert L.gymrs_default_params(_capi.MOUNTAIN_CAR, C.byref(m)) == 0
+    assert (m.min_position, m.max_position, m.max_speed, m.goal_position, m.goal_velocity, m.force,
+            m.gravity) == (-1.2, 0.6, 0.07, 0.5, 0.0, 0.001, 0.0025)
+    assert L.gymrs_default_params(7, C.byref(m)) == _capi.ERR_BAD_ARG
+
+
+def test_no_cpu_fallback_without_a_device():
+    from gym_rs_b200 import _capi
+    L = _capi.load()
+    if L.gymrs_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    h = C.c_void_p()
+    rc = L.gymrs_create(_capi.CARTPOLE, 16, 0, 0, None, 0, C.byref(h))
+    assert rc == _capi.ERR_NO_DEVICE and not h.value
+    assert b"no CUDA device" in L.gymrs_last_error()
+    import gym_rs_b200
+    with pytest.raises(_capi.GymrsError):
+        gym_rs_b200.CartPoleEnv()
+
+
+def test_bad_arguments_return_codes_not_crashes():
+    from gym_rs_b200 import _capi
+    L = _capi.load()
+    assert L.gymrs_create(_capi.CARTPOLE, 16, 0, 0, None, 0, None) == _capi.ERR_BAD_ARG
+    h = C.c_void_p()
+    assert L.gymrs_create(99, 16, 0, 0, None, 0, C.byref(h)) == _capi.ERR_BAD_ARG
+    assert L.gymrs_create(_capi.CARTPOLE, 0, 0, 0, None, 0, C.byref(h)) == _capi.ERR_BAD_ARG
+    assert L.gymrs_step(None, None, 0) == _capi.ERR_BAD_ARG
+    assert L.gymrs_sync(None, None) == _capi.ERR_BAD_ARG
+    assert L.gymrs_destroy(None) == 0
+
+
+def test_product_package_never_references_the_oracle():
+    pkg = os.path.join(ROOT, "gym_rs_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+                assert "gymrs_oracle" not in txt and "orc_" not in txt, f
+    hdr = open(os.path.join(ROOT, "include", "gymrs_b200.h")).read()
+    assert "orc_" not in hdr
+    out = subprocess.run(["ldd", os.path.join(pkg, "libgymrs_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+# ---- the reference's unit tests, through the C ABI / host mirror ----------------------
+
+def test_clip_reference_unit_tests():
+    from gym_rs_b200.utils.custom.util_fns import clip
+    assert clip(2, 0, 1) == 1      # util_fns.rs:16-20
+    assert clip(-1, 0, 1) == 0     # util_fns.rs:22-26
+    assert clip(1, -1, 2) == 1     # util_fns.rs:28-32
+    assert clip(0.08, -0.07, 0.07) == 0.07 and clip(-0.08, -0.07, 0.07) == -0.07
+
+
+def test_discrete_contains_reference_unit_tests():
+    from gym_rs_b200.spaces import Discrete
+    obj = Discrete(3)
+    assert not obj.contains(3) and not obj.contains(4)   # discrete.rs:27-33
+    assert obj.contains(1) and obj.contains(2)           # discrete.rs:35-41
+    assert not obj.contains(-1)
+
+
+def test_rand_random_reference_unit_tests():
+    from gym_rs_b200.utils.seeding import rand_random
+    _gen, seed = rand_random(42)   # seeding.rs:33-39
+    assert seed == 42
+    _gen, seed = rand_random(64)   # doctest seeding.rs:11-20
+    assert seed == 64
+    assert rand_random(None)[1] != rand_random(None)[1]
+
+
+def test_module_paths_follow_the_crate():
+    import gym_rs_b200
+    from gym_rs_b200.core import ActionReward, Env, EnvProperties, RewardRange  # noqa: F401
+    from gym_rs_b200.envs.classical_control.cartpole import CartPoleEnv, CartPoleObservation  # noqa: F401
+    from gym_rs_b200.envs.classical_control.mountain_car import MountainCarEnv, MountainCarObservation  # noqa: F401
+    from gym_rs_b200.spaces import BoxR, Discrete, Space  # noqa: F401
+    from gym_rs_b200.utils.renderer import RenderMode  # noqa: F401
+    assert issubclass(CartPoleEnv, Env) and issubclass(Env, EnvProperties)
+    rr = RewardRange()
+    assert rr.lower_bound == float("-inf") and rr.upper_bound == float("inf")   # core.rs:16-19
+    o = CartPoleObservation(1.0, 2.0, 3.0, 4.0)
+    assert (-o).to_vec() == [-1.0, -2.0, -3.0, -4.0]
+    assert gym_rs_b200.RenderMode.NONE.value == "none"

@@ -1,0 +1,744 @@
+"""GPU parity tests: the CUDA step path, called through the C ABI, against the f64 CPU oracle
+on identical inputs.
+
+Tolerance ("within 1e-6", BASELINE.json north_star):
+    |gpu - ref| <= 1e-6 * max(1, |ref|)        for every float output.
+done flags are compared wherever the f64 value is farther than 1e-6 from a termination
+threshold; inside that band f32 and f64 may legitimately disagree and are only counted.
+Integer / byte outputs (done outside the band, reward class, steps_beyond_terminated,
+truncated) and everything that is GPU-vs-GPU (rollout vs single steps, vec widths, sharding,
+host path vs device path) are compared bit-exactly.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6
+N_FULL = 1 << 20
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def g():
+    import gym_rs_b200
+    return gym_rs_b200
+
+
+def mixed_err(gpu, ref):
+    gpu = np.asarray(gpu, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return np.abs(gpu - ref) / np.maximum(1.0, np.abs(ref))
+
+
+def assert_within(gpu, ref, what, tol=TOL):
+    e = mixed_err(gpu, ref)
+    assert np.all(np.isfinite(np.asarray(gpu, dtype=np.float64))), what
+    assert e.max() <= tol, f"{what}: max mixed err {e.max():.3e} at {np.unravel_index(e.argmax(), e.shape)}"
+    return float(e.max())
+
+
+def dev_actions(torch, a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def cartpole_inputs(n, seed=0):
+    r = np.random.default_rng(seed)
+    st = np.stack([r.uniform(-2.4, 2.4, n), r.uniform(-3, 3, n), r.uniform(-0.21, 0.21, n),
+                   r.uniform(-3, 3, n)]).astype(np.float32)
+    act = r.integers(0, 2, n).astype(np.int32)
+    return st, act
+
+
+def mountain_car_inputs(n, seed=0):
+    r = np.random.default_rng(seed)
+    st = np.stack([r.uniform(-1.2, 0.6, n), r.uniform(-0.07, 0.07, n)]).astype(np.float32)
+    act = r.integers(0, 3, n).astype(np.int32)
+    return st, act
+
+
+def pendulum_inputs(n, seed=0):
+    r = np.random.default_rng(seed)
+    st = np.stack([r.uniform(-math.pi, math.pi, n), r.uniform(-8, 8, n)]).astype(np.float32)
+    act = r.uniform(-2.5, 2.5, n).astype(np.float32)
+    return st, act
+
+
+def cartpole_band(ref_state, p=None):
+    x, th = ref_state[0], ref_state[2]
+    thr_x, thr_th = 2.4, 12 * 2 * math.pi / 360
+    return (np.abs(np.abs(x) - thr_x) < 1e-6) | (np.abs(np.abs(th) - thr_th) < 1e-6)
+
+
+# --------------------------------------------------------------------------------------
+# single-step parity on 2^20 random (state, action) pairs
+# --------------------------------------------------------------------------------------
+
+def test_cartpole_single_step_parity_1m(torch, g):
+    st, act = cartpole_inputs(N_FULL)
+    env = g.CartPoleEnv(num_envs=N_FULL)
+    env.set_state(st)
+    out = env.step(dev_actions(torch, act))
+    env.sync()
+    ref = oracle.step_batch(oracle.CARTPOLE, st, act, sbt=np.full(N_FULL, -1))
+    got = out.observation.cpu().numpy()
+    worst = assert_within(got, ref["state"], "cartpole state")
+    assert np.array_equal(env.get_state(), got)  # observation IS the state
+    band = cartpole_band(ref["state"])
+    gd = out.done.cpu().numpy()
+    assert np.array_equal(gd[~band], ref["done"][~band])
+    assert band.sum() < 100
+    assert np.array_equal(out.reward.cpu().numpy(), ref["reward"].astype(np.float32))
+    assert not out.truncated.cpu().numpy().any()
+    sbt = env.steps_beyond_terminated.cpu().numpy()
+    assert np.array_equal(sbt[~band], ref["sbt"][~band])
+    assert 0.2 < ref["done"].mean() < 0.9  # the inputs exercise both outcomes
+    print(f"cartpole 1M single-step max mixed err {worst:.3e}, in-band {int(band.sum())}")
+    env.close()
+
+
+def test_mountain_car_single_step_parity_1m(torch, g):
+    st, act = mountain_car_inputs(N_FULL)
+    env = g.MountainCarEnv(num_envs=N_FULL)
+    env.set_state(st)
+    out = env.step(dev_actions(torch, act))
+    env.sync()
+    ref = oracle.step_batch(oracle.MOUNTAIN_CAR, st, act)
+    got = out.observation.cpu().numpy()
+    worst = assert_within(got, ref["state"], "mountain car state")
+    p, v = ref["state"]
+    band = (np.abs(p - 0.5) < 1e-6) | (np.abs(v) < 1e-6) | (np.abs(p + 1.2) < 1e-6)
+    assert np.array_equal(out.done.cpu().numpy()[~band], ref["done"][~band])
+    assert np.all(out.reward.cpu().numpy() == -1.0)
+    assert ref["done"].sum() > 1000
+    print(f"mountain car 1M single-step max mixed err {worst:.3e}, in-band {int(band.sum())}")
+    env.close()
+
+
+def test_pendulum_single_step_parity_1m(torch, g):
+    st, act = pendulum_inputs(N_FULL)
+    env = g.PendulumEnv(num_envs=N_FULL)
+    env.set_state(st)
+    out = env.step(dev_actions(torch, act))
+    env.sync()
+    ref = oracle.step_batch(oracle.PENDULUM, st, act)
+    worst = assert_within(out.observation.cpu().numpy(), ref["obs"], "pendulum obs")
+    assert_within(out.reward.cpu().numpy(), ref["reward"], "pendulum reward")
+    gs = env.get_state()
+    # stored theta is wrapped to [-pi, pi): compare modulo 2 pi
+    d = gs[0].astype(np.float64) - ref["state"][0]
+    d = d - 2 * math.pi * np.round(d / (2 * math.pi))
+    assert np.abs(d).max() <= 4e-6
+    assert np.abs(gs[0]).max() <= math.pi + 1e-6
+    assert_within(gs[1], ref["state"][1], "pendulum theta_dot")
+    assert not out.done.cpu().numpy().any()
+    print(f"pendulum 1M single-step max mixed err {worst:.3e}")
+    env.close()
+
+
+def test_cartpole_semi_implicit_integrator(torch, g):
+    n = 1 << 16
+    st, act = cartpole_inputs(n, seed=3)
+    env = g.CartPoleEnv(num_envs=n)
+    p = env.params
+    p.kinematics_integrator = 1
+    env.params = p
+    env.set_state(st)
+    out = env.step(dev_actions(torch, act))
+    env.sync()
+    op = oracle.default_params(oracle.CARTPOLE)
+    op.kinematics_integrator = 1
+    ref = oracle.step_batch(oracle.CARTPOLE, st, act, params=op)
+    assert_within(out.observation.cpu().numpy(), ref["state"], "semi-implicit state")
+    env.close()
+
+
+def test_mutated_pub_fields_take_effect(torch, g):
+    """The reference's constants are `pub` fields (cartpole.rs:63-80, mountain_car.rs:49-63)."""
+    n = 1 << 14
+    st, act = cartpole_inputs(n, seed=4)
+    env = g.CartPoleEnv(num_envs=n)
+    p = env.params
+    p.gravity, p.masspole, p.length, p.force_mag, p.tau = 3.7, 0.25, 0.8, 7.0, 0.01
+    p.x_threshold, p.theta_threshold_radians = 1.0, 0.1
+    env.params = p
+    env.set_state(st)
+    out = env.step(dev_actions(torch, act))
+    env.sync()
+    op = oracle.default_params(oracle.CARTPOLE)
+    op.gravity, op.masspole, op.length, op.force_mag, op.tau = 3.7, 0.25, 0.8, 7.0, 0.01
+    op.x_threshold, op.theta_threshold_radians = 1.0, 0.1
+    ref = oracle.step_batch(oracle.CARTPOLE, st, act, params=op)
+    assert_within(out.observation.cpu().numpy(), ref["state"], "mutated params state")
+    x, th = ref["state"][0], ref["state"][2]
+    band = (np.abs(np.abs(x) - 1.0) < 1e-6) | (np.abs(np.abs(th) - 0.1) < 1e-6)
+    assert np.array_equal(out.done.cpu().numpy()[~band], ref["done"][~band])
+    assert env.observation_space().high.x == 2.0
+    env.close()
+
+    st, act = mountain_car_inputs(n, seed=4)
+    env = g.MountainCarEnv(num_envs=n)
+    p = env.params
+    p.force, p.gravity, p.max_speed, p.goal_position = 0.002, 0.003, 0.05, 0.4
+    env.params = p
+    env.set_state(st)
+    out = env.step(dev_actions(torch, act))
+    env.sync()
+    op = oracle.default_params(oracle.MOUNTAIN_CAR)
+    op.force, op.gravity, op.max_speed, op.goal_position = 0.002, 0.003, 0.05, 0.4
+    ref = oracle.step_batch(oracle.MOUNTAIN_CAR, st, act, params=op)
+    assert_within(out.observation.cpu().numpy(), ref["state"], "mutated mountain car")
+    env.close()
+
+
+# --------------------------------------------------------------------------------------
+# golden vectors (tests/golden/step_vectors.json) through the GPU
+# --------------------------------------------------------------------------------------
+
+def test_golden_vectors_on_gpu(torch, g, golden):
+    for key, cls, kind in (("cartpole", g.CartPoleEnv, oracle.CARTPOLE),
+                           ("mountain_car", g.MountainCarEnv, oracle.MOUNTAIN_CAR)):
+        vecs = golden[key]
+        st = np.array([v["state"] for v in vecs], dtype=np.float64).T
+        act = np.array([v["action"] for v in vecs], dtype=np.int32)
+        env = cls(num_envs=len(vecs))
+        env.set_state(st.astype(np.float32))
+        out = env.step(dev_actions(torch, act))
+        env.sync()
+        got = out.observation.cpu().numpy()
+        want = np.array([v["next_state_mp"] for v in vecs]).T
+        # inputs were rounded to f32 first, so allow the propagated input rounding (<= 2e-7)
+        assert_within(got, want, key, tol=1.5e-6)
+        ref = oracle.step_batch(kind, st.astype(np.float32), act)
+        assert_within(got, ref["state"], key + " (same f32 inputs)")
+        env.close()
+    vecs = golden["pendulum"]
+    st = np.array([v["state"] for v in vecs], dtype=np.float32).T
+    act = np.array([v["action"] for v in vecs], dtype=np.float32)
+    env = g.PendulumEnv(num_envs=len(vecs))
+    env.set_state(st)
+    out = env.step(dev_actions(torch, act))
+    env.sync()
+    ref = oracle.step_batch(oracle.PENDULUM, st, act)
+    assert_within(out.observation.cpu().numpy(), ref["obs"], "pendulum golden obs")
+    assert_within(out.reward.cpu().numpy(), ref["reward"], "pendulum golden reward")
+    env.close()
+
+
+def test_appendix_b_exact_cases(torch, g):
+    """Hand-checked boundary cases: termination by x / theta, wall rule, goal, clip."""
+    env = g.CartPoleEnv(num_envs=4)
+    st = np.array([[0, 0, 0, 0], [2.39, 1.0, 0, 0], [0, 0, 0.2, 1.5], [-2.39, -1.0, 0, 0]], dtype=np.float32).T
+    env.set_state(st)
+    out = env.step(dev_actions(torch, np.array([1, 1, 0, 0], dtype=np.int32)))
+    env.sync()
+    o = out.observation.cpu().numpy()
+    assert abs(o[1, 0] - 0.3414634146341463) < 1e-6 and abs(o[3, 0] + 0.2926829268292683) < 1e-6
+    assert list(out.done.cpu().numpy()) == [0, 1, 1, 1]
+    assert list(out.reward.cpu().numpy()) == [1.0, 1.0, 1.0, 1.0]
+    env.close()
+
+    env = g.MountainCarEnv(num_envs=5)
+    st = np.array([[-1.2, -0.05], [-1.19, -0.07], [0.49, 0.07], [0.6, 0.07], [-0.5, 0.0]], dtype=np.float32).T
+    env.set_state(st)
+    out = env.step(dev_actions(torch, np.array([0, 0, 2, 2, 1], dtype=np.int32)))
+    env.sync()
+    o = out.observation.cpu().numpy()
+    assert o[0, 0] == np.float32(-1.2) and o[1, 0] == 0.0   # wall rule, mountain_car.rs:418-420
+    assert o[0, 1] == np.float32(-1.2) and o[1, 1] == 0.0   # clip then wall rule
+    assert abs(o[0, 2] - 0.56) < 1e-6 and o[1, 2] == np.float32(0.07)
+    assert o[0, 3] == np.float32(0.6)                        # clipped to max_position
+    assert abs(o[0, 4] + 0.5001768430041692) < 1e-6
+    assert list(out.done.cpu().numpy()) == [0, 0, 1, 1, 0]
+    env.close()
+
+
+# --------------------------------------------------------------------------------------
+# closed loop with per-step resync: the oracle is fed the device's f32 state each step
+# --------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind", ["cartpole", "mountain_car", "pendulum"])
+def test_closed_loop_trajectory_parity(torch, g, kind):
+    n, steps = 1 << 15, 200
+    r = np.random.default_rng(11)
+    if kind == "cartpole":
+        env, ok = g.CartPoleEnv(num_envs=n), oracle.CARTPOLE
+    elif kind == "mountain_car":
+        env, ok = g.MountainCarEnv(num_envs=n), oracle.MOUNTAIN_CAR
+    else:
+        env, ok = g.PendulumEnv(num_envs=n), oracle.PENDULUM
+    env.reset(seed=5)
+    worst = 0.0
+    sbt = np.full(n, -1, dtype=np.int64)
+    disagreements = 0
+    for t in range(steps):
+        st = env.get_state()
+        if kind == "pendulum":
+            act = r.uniform(-2, 2, n).astype(np.float32)
+        else:
+            act = r.integers(0, 2 if kind == "cartpole" else 3, n).astype(np.int32)
+        out = env.step(dev_actions(torch, act))
+        env.sync()
+        ref = oracle.step_batch(ok, st, act, sbt=sbt if kind == "cartpole" else None)
+        if kind == "pendulum":
+            worst = max(worst, assert_within(out.observation.cpu().numpy(), ref["obs"], f"{kind} t={t}"))
+            assert_within(out.reward.cpu().numpy(), ref["reward"], f"{kind} reward t={t}")
+        else:
+            worst = max(worst, assert_within(out.observation.cpu().numpy(), ref["state"], f"{kind} t={t}"))
+            gd = out.done.cpu().numpy()
+            diff = gd != ref["done"]
+            if kind == "cartpole":
+                assert not (diff & ~cartpole_band(ref["state"])).any()
+                gs = env.steps_beyond_terminated.cpu().numpy()
+                sbt = gs.astype(np.int64)  # resync
+                rr = out.reward.cpu().numpy()
+                assert np.array_equal(rr[~diff], ref["reward"][~diff].astype(np.float32))
+            disagreements += int(diff.sum())
+    assert disagreements < 20
+    if kind == "cartpole":
+        # without reset practically every pole has fallen: steps_beyond_terminated is Some(_)
+        assert (sbt >= 0).mean() > 0.99
+    print(f"{kind} closed loop {steps} steps: max mixed err {worst:.3e}, in-band done flips {disagreements}")
+    env.close()
+
+
+def test_cartpole_reward_sequence_after_termination(torch, g, golden):
+    """cartpole.rs:455-464 through the device: 1.0, ..., 1.0 (first done), 0.0, 0.0, ..."""
+    seq = golden["cartpole_reward_sequence"]
+    env = g.CartPoleEnv(num_envs=3)
+    env.set_state(np.zeros((4, 3), dtype=np.float32))
+    ones = dev_actions(torch, np.ones(3, dtype=np.int32))
+    for i, v in enumerate(seq):
+        out = env.step(ones)
+        env.sync()
+        assert bool(out.done.cpu().numpy()[0]) == v["done"], i
+        assert float(out.reward.cpu().numpy()[0]) == v["reward"], i
+        assert_within(out.observation.cpu().numpy()[:, 0], v["state"], f"step {i}", tol=1e-5)
+    assert int(env.steps_beyond_terminated.cpu().numpy()[0]) > 0
+    env.close()
+
+
+# --------------------------------------------------------------------------------------
+# reset
+# --------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind", ["cartpole", "mountain_car", "pendulum"])
+def test_reset_matches_oracle_philox_stream(torch, g, kind):
+    n = 100003
+    cls, ok = {"cartpole": (g.CartPoleEnv, oracle.CARTPOLE), "mountain_car": (g.MountainCarEnv, oracle.MOUNTAIN_CAR),
+               "pendulum": (g.PendulumEnv, oracle.PENDULUM)}[kind]
+    env = cls(num_envs=n, global_env_offset=12345)
+    obs, info = env.reset(seed=42, return_info=True)
+    assert info == ()
+    st = env.get_state()
+    ref = oracle.reset_batch(ok, n, seed=42, global_env_offset=12345)
+    assert np.abs(st - ref).max() <= 1e-7 * max(1.0, np.abs(ref).max())
+    # a reset is a pure function of the seed, like re-seeding PCG64 in the reference
+    env.reset(seed=42)
+    assert np.array_equal(env.get_state(), st)
+    env.reset(seed=43)
+    assert not np.array_equal(env.get_state(), st)
+    _, info = env.reset()
+    assert info is None and env.rand_random()[1] not in (42, 43)
+    if kind == "cartpole":
+        assert st.min() >= -0.05 and st.max() < 0.05
+        assert abs(st.mean()) < 1e-3 and abs(st.std() - 0.1 / math.sqrt(12)) < 1e-3
+    elif kind == "mountain_car":
+        assert st[0].min() >= -0.6 and st[0].max() < -0.4 and np.all(st[1] == 0)
+    else:
+        assert st[0].min() >= -math.pi - 1e-6 and st[0].max() <= math.pi and np.abs(st[1]).max() <= 1
+        o = obs.cpu().numpy()
+        assert_within(o[0], np.cos(st[0].astype(np.float64)), "reset cos")
+        assert_within(o[1], np.sin(st[0].astype(np.float64)), "reset sin")
+    env.close()
+
+
+def test_reset_options_and_mask(torch, g):
+    n = 4096
+    env = g.CartPoleEnv(num_envs=n)
+    lo = g.CartPoleObservation(1, 2, 3, 4)
+    hi = g.CartPoleObservation(2, 3, 4, 5)
+    env.reset(seed=9, options=g.BoxR(lo, hi))
+    st = env.get_state()
+    for k in range(4):
+        assert st[k].min() >= k + 1 and st[k].max() < k + 2
+    ref = oracle.reset_batch(oracle.CARTPOLE, n, seed=9, low=[1, 2, 3, 4], high=[2, 3, 4, 5])
+    assert np.abs(st - ref).max() < 1e-6
+    mask = np.zeros(n, dtype=np.uint8)
+    mask[::3] = 1
+    env.reset(seed=10, mask=torch.as_tensor(mask).cuda())
+    st2 = env.get_state()
+    assert np.array_equal(st2[:, mask == 0], st[:, mask == 0])
+    assert np.abs(st2[:, mask == 1]).max() < 0.05  # options apply to one call only
+    env.close()
+    # mountain car ignores velocity bounds (mountain_car.rs:162-167)
+    mc = g.MountainCarEnv(num_envs=n)
+    mc.reset(seed=1, options=g.BoxR(g.MountainCarObservation(0.1, 0.01), g.MountainCarObservation(0.2, 0.05)))
+    st = mc.get_state()
+    assert st[0].min() >= 0.1 and st[0].max() < 0.2 and np.all(st[1] == 0)
+    mc.close()
+
+
+def test_autoreset_resamples_done_envs_like_the_oracle(torch, g):
+    n = 1 << 16
+    st, act = cartpole_inputs(n, seed=21)
+    env = g.CartPoleEnv(num_envs=n, global_env_offset=1000)
+    env.reset(seed=77)
+    env.set_state(st)
+    out = env.step(dev_actions(torch, act), autoreset=True)
+    env.sync()
+    ref = oracle.step_batch(oracle.CARTPOLE, st, act)
+    gd = out.done.cpu().numpy().astype(bool)
+    band = cartpole_band(ref["state"])
+    assert np.array_equal(gd[~band], ref["done"][~band].astype(bool))
+    got = out.observation.cpu().numpy()
+    assert_within(got[:, ~gd], ref["state"][:, ~gd], "surviving envs")
+    # done envs hold a fresh state: Philox(seed, global id, epoch = step index + 1)
+    fresh = oracle.reset_batch(oracle.CARTPOLE, n, seed=77, global_env_offset=1000, epoch=1)
+    assert np.abs(got[:, gd] - fresh[:, gd]).max() <= 1e-7
+    assert np.all(out.reward.cpu().numpy() == 1.0)
+    assert (env.steps_beyond_terminated.cpu().numpy() == -1).all()
+    # the next step draws from the next epoch
+    st2 = env.get_state()
+    out = env.step(dev_actions(torch, act), autoreset=True)
+    env.sync()
+    gd2 = out.done.cpu().numpy().astype(bool)
+    fresh2 = oracle.reset_batch(oracle.CARTPOLE, n, seed=77, global_env_offset=1000, epoch=2)
+    assert gd2.any()
+    assert np.abs(out.observation.cpu().numpy()[:, gd2] - fresh2[:, gd2]).max() <= 1e-7
+    ref2 = oracle.step_batch(oracle.CARTPOLE, st2, act)
+    assert_within(out.observation.cpu().numpy()[:, ~gd2], ref2["state"][:, ~gd2], "second step")
+    env.close()
+
+
+def test_long_autoreset_rollout_stays_in_the_live_region(torch, g):
+    """1M envs x 300 random-action steps with auto-reset: every state stays finite and inside
+    the live region plus one step; episode statistics match the oracle's scalar loop."""
+    n = N_FULL
+    env = g.CartPoleEnv(num_envs=n)
+    env.reset(seed=0)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    dones = 0
+    steps = 300
+    for t in range(steps):
+        act = torch.randint(0, 2, (n,), generator=gen, device="cuda", dtype=torch.int32)
+        out = env.step(act, autoreset=True)
+        dones += int(out.done.sum().item())
+    env.sync()
+    st = env.get_state()
+    assert np.isfinite(st).all()
+    assert np.abs(st[0]).max() <= 2.4 + 1e-6 and np.abs(st[2]).max() <= 0.2095
+    mean_len = n * steps / dones
+    # reference dynamics under uniform random actions: mean episode length ~22 steps
+    assert 18.0 < mean_len < 27.0, mean_len
+    env.close()
+
+
+# --------------------------------------------------------------------------------------
+# GPU-vs-GPU invariants (bit-exact)
+# --------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind", ["cartpole", "mountain_car", "pendulum"])
+def test_vec_widths_and_ragged_sizes_are_bit_identical(torch, g, kind):
+    n = 100003  # not a multiple of 4: exercises the scalar tail
+    cls = {"cartpole": g.CartPoleEnv, "mountain_car": g.MountainCarEnv, "pendulum": g.PendulumEnv}[kind]
+    r = np.random.default_rng(5)
+    if kind == "pendulum":
+        acts = [dev_actions(torch, r.uniform(-2, 2, n).astype(np.float32)) for _ in range(6)]
+    else:
+        acts = [dev_actions(torch, r.integers(0, 2, n).astype(np.int32)) for _ in range(6)]
+    results = []
+    for vec, block in ((4, 256), (2, 128), (1, 64), (0, 0)):
+        env = cls(num_envs=n, time_limit=True)
+        env.set_launch_config(vec=vec, block=block, pdl=1)
+        env.reset(seed=3)
+        for a in acts:
+            out = env.step(a, autoreset=True)
+        env.sync()
+        results.append((env.get_state(), out.observation.cpu().numpy(), out.reward.cpu().numpy(),
+                        out.done.cpu().numpy(), out.truncated.cpu().numpy()))
+        env.close()
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert np.array_equal(a, b)
+
+
+def test_unaligned_action_pointer_falls_back_to_scalar_lanes(torch, g):
+    n = 8192
+    st, act = cartpole_inputs(n + 1, seed=8)
+    big = dev_actions(torch, act)
+    env = g.CartPoleEnv(num_envs=n)
+    env.set_state(st[:, 1:])
+    out = env.step(big[1:], autoreset=False)  # 4-byte aligned only
+    env.sync()
+    ref = oracle.step_batch(oracle.CARTPOLE, st[:, 1:], act[1:])
+    assert_within(out.observation.cpu().numpy(), ref["state"], "unaligned actions")
+    env.close()
+
+
+@pytest.mark.parametrize("kind", ["cartpole", "mountain_car", "pendulum"])
+def test_rollout_equals_single_steps(torch, g, kind):
+    n, k = 50001, 17
+    cls = {"cartpole": g.CartPoleEnv, "mountain_car": g.MountainCarEnv, "pendulum": g.PendulumEnv}[kind]
+    r = np.random.default_rng(6)
+    if kind == "pendulum":
+        acts = dev_actions(torch, r.uniform(-2, 2, (k, n)).astype(np.float32))
+    else:
+        acts = dev_actions(torch, r.integers(0, 2, (k, n)).astype(np.int32))
+    a = cls(num_envs=n)
+    b = cls(num_envs=n)
+    a.reset(seed=2)
+    b.reset(seed=2)
+    od = a.obs_dim
+    obs_out = torch.zeros((k, od, n), device="cuda")
+    rew_out = torch.zeros((k, n), device="cuda")
+    done_out = torch.zeros((k, n), device="cuda", dtype=torch.uint8)
+    a.rollout(acts, obs_out, rew_out, done_out, autoreset=True)
+    a.sync()
+    for t in range(k):
+        out = b.step(acts[t], autoreset=True)
+        assert torch.equal(out.observation, obs_out[t]), t
+        assert torch.equal(out.reward, rew_out[t]), t
+        assert torch.equal(out.done, done_out[t]), t
+    b.sync()
+    assert np.array_equal(a.get_state(), b.get_state())
+    # and the two handles keep agreeing afterwards (same epoch counter)
+    o1 = a.step(acts[0], autoreset=True).observation.clone()
+    o2 = b.step(acts[0], autoreset=True).observation.clone()
+    assert torch.equal(o1, o2)
+    a.close()
+    b.close()
+
+
+def test_step_host_equals_device_step(torch, g):
+    n = (1 << 19) + 777  # several pipeline chunks + ragged tail
+    st, act = cartpole_inputs(n, seed=9)
+    a = g.CartPoleEnv(num_envs=n)
+    b = g.CartPoleEnv(num_envs=n)
+    for e in (a, b):
+        e.reset(seed=4)
+        e.set_state(st)
+    obs = torch.empty((4, n), dtype=torch.float32).pin_memory()
+    rew = torch.empty(n, dtype=torch.float32).pin_memory()
+    dn = torch.empty(n, dtype=torch.uint8).pin_memory()
+    tr = torch.empty(n, dtype=torch.uint8).pin_memory()
+    hact = torch.as_tensor(act).pin_memory()
+    for _ in range(3):
+        a.step_host(hact, obs, rew, dn, tr, autoreset=True)
+        out = b.step(dev_actions(torch, act), autoreset=True)
+        b.sync()
+        assert torch.equal(obs, out.observation.cpu())
+        assert torch.equal(rew, out.reward.cpu())
+        assert torch.equal(dn, out.done.cpu())
+        assert not tr.any()
+    # pageable numpy buffers work too
+    o2 = np.empty((4, n), dtype=np.float32)
+    r2 = np.empty(n, dtype=np.float32)
+    d2 = np.empty(n, dtype=np.uint8)
+    a.step_host(act, o2, r2, d2, None, autoreset=True)
+    out = b.step(dev_actions(torch, act), autoreset=True)
+    b.sync()
+    assert np.array_equal(o2, out.observation.cpu().numpy())
+    a.close()
+    b.close()
+
+
+def test_sharding_invariance_at_full_size(torch, g):
+    """results are keyed by GLOBAL env id, so one 1M-env handle and two
+    512K-env handles (as two GPUs would hold them) produce identical bits."""
+    n = N_FULL
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    acts = [torch.randint(0, 2, (n,), generator=gen, device="cuda", dtype=torch.int32) for _ in range(40)]
+    whole = g.CartPoleEnv(num_envs=n)
+    lo = g.CartPoleEnv(num_envs=n // 2, global_env_offset=0)
+    hi = g.CartPoleEnv(num_envs=n // 2, global_env_offset=n // 2)
+    for e in (whole, lo, hi):
+        e.reset(seed=123)
+    for a in acts:
+        ow = whole.step(a, autoreset=True)
+        ol = lo.step(a[: n // 2], autoreset=True)
+        oh = hi.step(a[n // 2:], autoreset=True)
+    for e in (whole, lo, hi):
+        e.sync()
+    assert torch.equal(ow.observation[:, : n // 2], ol.observation)
+    assert torch.equal(ow.observation[:, n // 2:], oh.observation)
+    assert torch.equal(ow.done[: n // 2], ol.done) and torch.equal(ow.done[n // 2:], oh.done)
+    # checksum of checksums: the whole-batch sum equals the sum of the shard sums exactly (u8 counts)
+    assert int(ow.done.sum()) == int(ol.done.sum()) + int(oh.done.sum())
+    for e in (whole, lo, hi):
+        e.close()
+
+
+def test_determinism_same_seed_same_bits(torch, g):
+    n = 1 << 18
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    acts = [torch.randint(0, 3, (n,), generator=gen, device="cuda", dtype=torch.int32) for _ in range(25)]
+    outs = []
+    for _ in range(2):
+        env = g.MountainCarEnv(num_envs=n)
+        env.reset(seed=99)
+        for a in acts:
+            out = env.step(a, autoreset=True)
+        env.sync()
+        outs.append(out.observation.clone())
+        env.close()
+    assert torch.equal(outs[0], outs[1])
+
+
+# --------------------------------------------------------------------------------------
+# errors, time limit, clone, properties, scalar Env surface
+# --------------------------------------------------------------------------------------
+
+def test_invalid_action_is_reported_and_env_left_untouched(torch, g):
+    n = 4096
+    st, act = cartpole_inputs(n, seed=12)
+    act[1234] = 2    # not in Discrete(2)
+    act[99] = -1     # not a usize
+    env = g.CartPoleEnv(num_envs=n, global_env_offset=500)
+    env.set_state(st)
+    out = env.step(dev_actions(torch, act))
+    with pytest.raises(AssertionError, match="invalid"):
+        env.sync()
+    env.sync()  # sticky flag is cleared once reported
+    got = out.observation.cpu().numpy()
+    assert np.array_equal(got[:, 1234], st[:, 1234]) and np.array_equal(got[:, 99], st[:, 99])
+    ok = np.ones(n, dtype=bool)
+    ok[[99, 1234]] = False
+    a2 = act.copy()
+    a2[~ok] = 0
+    ref = oracle.step_batch(oracle.CARTPOLE, st, a2)
+    assert_within(got[:, ok], ref["state"][:, ok], "valid envs still stepped")
+    env.close()
+    mc = g.MountainCarEnv(num_envs=8)
+    mc.step(dev_actions(torch, np.array([0, 1, 2, 3, 0, 1, 2, 0], dtype=np.int32)))
+    with pytest.raises(AssertionError):
+        mc.sync()
+    mc.close()
+
+
+def test_time_limit_truncation(torch, g):
+    n = 2048
+    env = g.MountainCarEnv(num_envs=n, time_limit=True)
+    p = env.params
+    p.max_episode_steps = 7
+    env.params = p
+    env.reset(seed=1)
+    a = dev_actions(torch, np.ones(n, dtype=np.int32))
+    for t in range(1, 8):
+        out = env.step(a, autoreset=True)
+        env.sync()
+        tr = out.truncated.cpu().numpy()
+        assert tr.all() == (t == 7) and tr.any() == (t == 7)
+    st = env.get_state()
+    assert st[0].min() >= -0.6 and st[0].max() < -0.4 and np.all(st[1] == 0)  # truncated envs were reset
+    out = env.step(a, autoreset=True)
+    env.sync()
+    assert not out.truncated.cpu().numpy().any()
+    env.close()
+    # default (reference behaviour): never truncated (cartpole.rs:480, mountain_car.rs:432)
+    env = g.MountainCarEnv(num_envs=n)
+    for _ in range(250):
+        out = env.step(a)
+    env.sync()
+    assert not out.truncated.cpu().numpy().any()
+    env.close()
+
+
+def test_clone_is_a_deep_copy(torch, g):
+    n = 10000
+    env = g.CartPoleEnv(num_envs=n)
+    env.reset(seed=5)
+    a = dev_actions(torch, np.ones(n, dtype=np.int32))
+    env.step(a)
+    twin = env.clone()
+    s0 = env.get_state()
+    assert np.array_equal(twin.get_state(), s0)
+    env.step(a)
+    assert np.array_equal(twin.get_state(), s0)
+    o1 = twin.step(a).observation.cpu().numpy()
+    env.sync()
+    assert np.array_equal(o1, env.get_state())
+    d = env.serialize()
+    assert d["num_envs"] == n and len(d["state"]) == 4 and d["params"]["gravity"] == 9.8
+    env.close()
+    twin.close()
+
+
+def test_env_properties(torch, g):
+    cp = g.CartPoleEnv()
+    assert cp.action_space() == g.Discrete(2)                      # cartpole.rs:112
+    hi = cp.observation_space().high
+    assert hi.to_vec() == [4.8, math.inf, 0.41887902047863906, math.inf]   # cartpole.rs:105-113
+    assert cp.observation_space().low == -hi
+    assert cp.reward_range() == g.RewardRange(-math.inf, math.inf)  # core.rs:16-19
+    assert cp.render_mode() == g.RenderMode.NONE and cp.metadata().render_fps == 50
+    cp.close()
+    mc = g.MountainCarEnv()
+    assert mc.action_space() == g.Discrete(3)                      # mountain_car.rs:363
+    sp = mc.observation_space()
+    assert sp.low.to_vec() == [-1.2, -0.07] and sp.high.to_vec() == [0.6, 0.07]  # :353-354
+    assert mc.metadata().render_fps == 30
+    mc.close()
+    pd = g.PendulumEnv()
+    assert pd.action_space() == g.BoxR(-2.0, 2.0)
+    assert pd.observation_space().high.to_vec() == [1.0, 1.0, 8.0]
+    pd.close()
+    with pytest.raises(ValueError):
+        g.CartPoleEnv(g.RenderMode.Human)
+
+
+def test_scalar_env_surface_like_examples_cartpole(torch, g):
+    """BASELINE config 1 / examples/cartpole.rs:7-33 with RenderMode::None: one env, random actions,
+    15 episodes of <= 475 steps, reset after each; cross-checked step by step with the oracle."""
+    import random
+    rng = random.Random(0)
+    env = g.CartPoleEnv(g.RenderMode.NONE)
+    env.reset(None, False, None)
+    rewards = []
+    total_steps = 0
+    for ep in range(15):
+        state, _ = env.reset(seed=ep)
+        o = oracle.CartPoleEnv()
+        oracle.lib().orc_cartpole_new(oracle.C.byref(o))
+        for k, v in enumerate(state.to_vec()):
+            o.state[k] = v
+        current_reward = 0.0
+        for _ in range(475):
+            action = rng.randrange(2)
+            sr = env.step(action)
+            rew, dn, tr = oracle.C.c_double(), oracle.C.c_int(), oracle.C.c_int()
+            oracle.lib().orc_cartpole_step(oracle.C.byref(o), action, oracle.C.byref(rew),
+                                           oracle.C.byref(dn), oracle.C.byref(tr))
+            assert_within(sr.observation.to_vec(), list(o.state), "scalar step")
+            for k, v in enumerate(sr.observation.to_vec()):
+                o.state[k] = v  # resync
+            assert sr.reward == rew.value and sr.truncated is False and sr.info == ()
+            current_reward += sr.reward
+            total_steps += 1
+            if sr.done:
+                assert env.steps_beyond_terminated == 0
+                break
+        rewards.append(current_reward)
+    assert len(rewards) == 15 and all(5 <= r <= 475 for r in rewards)
+    with pytest.raises(AssertionError, match="2 usize invalid"):   # cartpole.rs:402-406
+        env.step(2)
+    env.close()
+    mc = g.MountainCarEnv(g.RenderMode.NONE)
+    mc.reset(seed=0)
+    sr = mc.step(1)
+    assert sr.reward == -1.0 and sr.done is False and sr.info is None
+    with pytest.raises(AssertionError, match=r"3 \(usize\) invalid"):  # mountain_car.rs:402-406
+        mc.step(3)
+    mc.close()
