@@ -34,6 +34,8 @@ RING = 16
 # algorithmic bytes per env-step
 ALGO_BYTES = {"cartpole": 41, "mountain_car": 25, "pendulum": 37}
 FOOTPRINT = {"cartpole": 25, "mountain_car": 17, "pendulum": 29}  # resident bytes per env of one batch
+ACTION_SETS = 8  # pre-generated action batches per ring slot
+ROLLOUT_BYTES = {"cartpole": 25, "mountain_car": 17, "pendulum": 21}  # action in + obs, reward, done out
 D2H_BYTES = {"cartpole": 21, "mountain_car": 13, "pendulum": 17}  # obs + reward + done
 WORKLOAD = {
     "cartpole": "CartPole-v1 1,048,576 envs/GPU, f32 SoA state, discrete int32 action, auto-reset",
@@ -58,6 +60,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--streams", type=int, default=1,
+                    help="experimental: ring slots alternate over this many CUDA streams")
+    ap.add_argument("--burn-in", type=int, default=300, help="untimed steps per ring slot before warm-up")
+    ap.add_argument("--rollout-steps", type=int, default=64, help="0 disables the fused-rollout extra")
     return ap.parse_args()
 
 
@@ -217,19 +223,27 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=device)
     n, K, W, env = args.envs, args.steps, args.warmup, args.env
     L = _capi.load()
-    stream = torch.cuda.current_stream(device)
+    # One dedicated (non-default) stream carries everything: the handles adopt torch's current
+    # stream, and the CUDA events that time the run are recorded on that same stream.
+    stream = torch.cuda.Stream(device)
+    torch.cuda.set_stream(stream)
 
     # ring of independent batches: rank r owns global env ids [r * n, (r + 1) * n) of every ring slot
     gen = torch.Generator(device=device).manual_seed(1 + rank)
+    streams = [stream] + [torch.cuda.Stream(device) for _ in range(max(args.streams, 1) - 1)]
     ring = []
     for j in range(args.ring):
         e = make_env(g, env, n, local_rank, (j * world + rank) * n)
-        e.set_stream(stream.cuda_stream)
+        e.set_stream(streams[j % len(streams)].cuda_stream)
         e.set_launch_config(vec=args.vec, block=args.block, pdl=args.pdl)
         e.reset(seed=0)
-        ring.append((e, make_actions(torch, env, n, device, gen)))
+        # ACTION_SETS pre-generated action batches per ring slot, used in rotation, so an env does
+        # not see the same action at every step
+        ring.append((e, [make_actions(torch, env, n, device, gen) for _ in range(ACTION_SETS)]))
     torch.cuda.synchronize(device)
-    handles = [(e.handle, a.data_ptr()) for e, a in ring]
+    # launch schedule: consecutive steps go to consecutive ring slots; visit v of a slot uses action set v
+    handles = [(e.handle, acts[v].data_ptr()) for v in range(ACTION_SETS) for e, acts in ring]
+    resident_pool = [(ring[0][0].handle, a.data_ptr()) for a in ring[0][1]]
     step = L.gymrs_step
     AR = _capi.STEP_AUTORESET
 
@@ -246,14 +260,39 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    def fork(ev):  # extra streams (if any) start after ev ...
+        for s in streams[1:]:
+            s.wait_event(ev)
+
+    def join():    # ... and the main stream's end event waits for all of them
+        for s in streams[1:]:
+            e_ = torch.cuda.Event()
+            e_.record(s)
+            stream.wait_event(e_)
+
+    # Burn-in (untimed, not part of warm-up): all envs start from a synchronised reset, so their
+    # first episodes end in a burst; a few hundred steps per slot decorrelate the episode phases
+    # and bring the per-step reset rate to its stationary value.
+    run_steps(args.burn_in * len(handles) // ACTION_SETS, handles)
+    barrier()
+
+    wall = []
+
     def timed(k, pool):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        w0 = time.perf_counter()
         ev0.record(stream)
+        fork(ev0)
         run_steps(k, pool)
+        join()
         ev1.record(stream)
         barrier()
+        wall.append((time.perf_counter() - w0) * 1e3)
         ms = ev0.elapsed_time(ev1)
+        # the device time must account for the host wall time of the same region (launch until
+        # drained); if it does not, the events were not on the stream the kernels ran on
+        assert ms > 0.7 * wall[-1] or wall[-1] < 0.2, (ms, wall[-1])
         if world > 1:
             t = torch.tensor([ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -267,7 +306,7 @@ def run_b200(args):
     repeats = int(min(25, max(3, 600.0 / max(est, 1e-3))))
     with ClockSampler(local_rank) as cs:
         times = [timed(K, handles) for _ in range(repeats)]
-        resident = [timed(K, handles[:1]) for _ in range(3)]
+        resident = [timed(K, resident_pool) for _ in range(3)]
     ms = statistics.median(times)
     clocks = cs.summary()
     for e, _ in ring:
@@ -283,7 +322,7 @@ def run_b200(args):
     if not args.no_e2e:
         e0 = ring[0][0]
         act_dtype = torch.float32 if env == "pendulum" else torch.int32
-        h_act = ring[0][1].cpu().to(act_dtype).pin_memory()
+        h_act = ring[0][1][0].cpu().to(act_dtype).pin_memory()
         h_obs = torch.empty((e0.obs_dim, n), dtype=torch.float32).pin_memory()
         h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
         h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -303,6 +342,44 @@ def run_b200(args):
         e2e = {"value": world * n * args.e2e_steps / dt, "unit": "env-steps/s",
                "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": D2H_BYTES[env] * n,
                "steps": args.e2e_steps, "api": "gymrs_step_host (pinned host actions in; obs, reward, done out)"}
+
+    # ---- fused rollout (labelled separately; never mixed with the single-step figure) ----------
+    rollout = None
+    if args.rollout_steps > 0:
+        e0 = ring[0][0]
+        kr = args.rollout_steps
+        if env == "pendulum":
+            acts = torch.rand((kr, n), generator=gen, device=device) * 4.0 - 2.0
+        else:
+            acts = torch.randint(0, 2 if env == "cartpole" else 3, (kr, n), generator=gen, device=device,
+                                 dtype=torch.int32)
+        obs_out = torch.empty((kr, e0.obs_dim, n), device=device)
+        rew_out = torch.empty((kr, n), device=device)
+        done_out = torch.empty((kr, n), device=device, dtype=torch.uint8)
+        for _ in range(3):
+            e0.rollout(acts, obs_out, rew_out, done_out, autoreset=True)
+        reps = []
+        for _ in range(7):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            ev0.record(stream)
+            e0.rollout(acts, obs_out, rew_out, done_out, autoreset=True)
+            ev1.record(stream)
+            barrier()
+            reps.append(ev0.elapsed_time(ev1))
+        e0.sync()
+        rms = statistics.median(reps)
+        if world > 1:
+            t = torch.tensor([rms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rms = float(t.item())
+        rbytes = ROLLOUT_BYTES[env] + 2 * 4 * e0.state_dim / kr
+        rollout = {"value": world * n * kr / (rms * 1e-3), "unit": "env-steps/s", "steps_per_launch": kr,
+                   "ms_per_launch": rms, "algorithmic_bytes_per_env_step": rbytes,
+                   "achieved_gbs": rbytes * n * kr / (rms * 1e-3) / 1e9, "frac": rbytes * n * kr / (rms * 1e-3) / 1e9 / peak,
+                   "api": "gymrs_rollout: one launch, state in registers, actions in / obs, reward, done out per step "
+                          f"({kr * (ROLLOUT_BYTES[env]) * n / 1e6:.0f} MB streamed per launch, larger than L2)"}
+        del acts, obs_out, rew_out, done_out
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -330,6 +407,7 @@ def run_b200(args):
                          "frac": achieved / peak, "traffic": ncu_traffic(env), "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": ALGO_BYTES[env], "kernel": "step_kernel"},
             "cpu_baseline": cpu,
+            "rollout": rollout,
             "l2_resident": {"value": world * n * K / (statistics.median(resident) * 1e-3), "unit": "env-steps/s",
                             "ms_per_step": ms_res / K,
                             "note": "one 1M-env batch stepped back to back (state stays in the 126 MB L2); "

@@ -1,26 +1,31 @@
 """Build libgymrs_b200.so (CUDA kernels + C ABI) in-tree with nvcc for sm_100a.
 
-nvcc cross-compiles without a GPU, so this runs in the CPU container and on the GPU
-box alike.  The .so is git-ignored but travels to the GPU box with the repo snapshot.
+nvcc cross-compiles without a GPU, so this runs in the CPU container and on the GPU box alike.
+The translation units compile in parallel and are linked into one shared library.  The .so and
+objects are git-ignored but travel to the GPU box with the repo snapshot.
 """
 from __future__ import annotations
 
 import os
+import shlex
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "libgymrs_b200.so")
-SOURCES = ["kernels.cu", "capi.cu"]
-HEADERS = ["kernels.hpp", "envs.cuh", "philox.cuh", os.path.join(ROOT, "include", "gymrs_b200.h")]
+SOURCES = ["kernels_cartpole.cu", "kernels_mountain_car.cu", "kernels_pendulum.cu", "capi.cu"]
+HEADERS = ["kernels_impl.cuh", "kernels.hpp", "envs.cuh", "philox.cuh",
+           os.path.join(ROOT, "include", "gymrs_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    # no -use_fast_math: sincosf / division keep their IEEE-accurate paths (parity to 1e-6)
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    # no -use_fast_math: transcendental and division accuracy is chosen per call site (envs.cuh)
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -29,6 +34,11 @@ def _nvcc() -> str:
         if c and os.path.exists(c):
             return c
     raise RuntimeError("nvcc not found: cannot build the CUDA extension")
+
+
+def _extra() -> list:
+    """Extra nvcc flags for experiments, e.g. GYMRS_NVCC_EXTRA='-DGYMRS_STEP_MIN_CTAS=4'."""
+    return shlex.split(os.environ.get("GYMRS_NVCC_EXTRA", ""))
 
 
 def _stale() -> bool:
@@ -40,16 +50,27 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+def _run(cmd):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return r.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale() and not os.environ.get("GYMRS_NVCC_EXTRA"):
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = _nvcc()
+    flags = NVCC_FLAGS + _extra() + (["-Xptxas", "-v"] if verbose else [])
+    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    cmds = [[nvcc] + flags + ["-c", os.path.join(CSRC, s), "-o", o] for s, o in zip(SOURCES, objs)]
+    with ThreadPoolExecutor(max_workers=len(cmds)) as ex:
+        logs = list(ex.map(_run, cmds))
+    _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
+          "-o", LIB] + objs)
     if verbose:
-        print(r.stderr)
+        print("\n".join(logs))
     return LIB
 
 

@@ -121,6 +121,10 @@ class Env(EnvProperties):
                                          pp, flags, C.byref(self._h)))
         self._refresh_views()
         self._refresh_spaces()
+        # The device views above are torch tensors and callers produce actions with torch, so the
+        # handle must run in torch's stream order, not on its private non-blocking stream.
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- plumbing ------------------------------------------------------------------
     def _refresh_views(self):
@@ -164,7 +168,14 @@ class Env(EnvProperties):
         self._refresh_spaces()
 
     def set_stream(self, cuda_stream: Optional[int]):
-        _capi.check(self._L.gymrs_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """cuda_stream: a cudaStream_t as an integer (torch: stream.cuda_stream).  0 means CUDA's
+        legacy default stream (what torch uses unless told otherwise) and is passed as the
+        cudaStreamLegacy handle; None restores the handle's private stream."""
+        if cuda_stream is None:
+            ptr = 0
+        else:
+            ptr = int(cuda_stream) or 0x1  # cudaStreamLegacy
+        _capi.check(self._L.gymrs_set_stream(self._h, C.c_void_p(ptr)))
 
     def set_launch_config(self, vec: int = 0, block: int = 0, pdl: int = 1):
         _capi.check(self._L.gymrs_set_launch_config(self._h, vec, block, pdl))
@@ -314,6 +325,8 @@ class Env(EnvProperties):
         other._h = C.c_void_p()
         _capi.check(self._L.gymrs_clone(self._h, C.byref(other._h)))
         other._refresh_views()
+        import torch
+        other.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         return other
 
     def serialize(self):

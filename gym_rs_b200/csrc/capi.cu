@@ -92,6 +92,12 @@ struct gymrs_env {
     uint32_t *elapsed = nullptr;
     void *d_actions = nullptr; // staging for *_host entry points
     uint32_t *err_host = nullptr, *err_dev = nullptr;
+    // chained launches (kernels_impl.cuh): word [0] = "protocol broken", words [1..] = per-CTA flags
+    uint32_t *chain_mem = nullptr;
+    uint32_t chain_seq = 0;         // sequence number of the last step launched on this handle
+    bool chain_ok = false;          // flags describe the handle's current state for (chain_vec, chain_block)
+    int chain_vec = 0, chain_block = 0;
+    cudaStream_t chain_stream = nullptr;
 
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_streams[2] = {nullptr, nullptr};
@@ -182,6 +188,9 @@ BatchArgs base_args(const gymrs_env *e)
     a.seed = e->seed;
     a.epoch = e->step_count + 1;
     a.err = e->err_dev;
+    a.chain_flags = e->chain_mem + 1;
+    a.chain_seq = e->chain_seq;
+    a.chain = 0;
     return a;
 }
 
@@ -261,6 +270,7 @@ int free_env(gymrs_env *e)
     cudaFree(e->sbt);
     cudaFree(e->elapsed);
     cudaFree(e->d_actions);
+    cudaFree(e->chain_mem);
     if (e->err_host) cudaFreeHost(e->err_host);
     for (auto &s : e->copy_streams) if (s) cudaStreamDestroy(s);
     for (auto &v : e->ev) if (v) cudaEventDestroy(v);
@@ -301,6 +311,9 @@ int alloc_env(gymrs_env *e)
         CU(cudaMalloc(&e->elapsed, sizeof(uint32_t) * e->ld));
         CU(cudaMemsetAsync(e->elapsed, 0, sizeof(uint32_t) * e->ld, e->stream));
     }
+    const size_t chain_words = (size_t)((n + 31) / 32) + 2; // V = 1, 32-thread CTAs is the finest geometry
+    CU(cudaMalloc(&e->chain_mem, chain_words * sizeof(uint32_t)));
+    CU(cudaMemsetAsync(e->chain_mem, 0, chain_words * sizeof(uint32_t), e->stream));
     CU(cudaHostAlloc(&e->err_host, 4 * sizeof(uint32_t), cudaHostAllocMapped));
     std::memset(e->err_host, 0, 4 * sizeof(uint32_t));
     CU(cudaHostGetDevicePointer(&e->err_dev, e->err_host, 0));
@@ -525,6 +538,7 @@ int gymrs_reset(gymrs_env *e, const uint64_t *seed, const float *low, const floa
     fold_params(e);
     BatchArgs a = base_args(e);
     a.seed = s;
+    e->chain_ok = false;
     cudaError_t ce = do_reset(e, a, mask, e->stream);
     std::memcpy(e->reset_low, keep_lo, sizeof keep_lo);
     std::memcpy(e->reset_high, keep_hi, sizeof keep_hi);
@@ -544,7 +558,20 @@ int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
     CU(cudaSetDevice(e->device));
     BatchArgs a = base_args(e);
     a.actions = actions;
-    CU(do_step(e, a, make_opts(e, step_flags), e->stream, false));
+    const LaunchOpts o = make_opts(e, step_flags);
+    // Chained launch: this step may skip the grid-wide dependency on the previous launch when the
+    // handle's per-CTA flags describe its current state for exactly this CTA -> env mapping.
+    const int v = pick_vec(a, o.vec, false), blk = pick_block(o);
+    a.chain_seq = ++e->chain_seq;
+    a.chain = (o.pdl == 2 && e->chain_ok && e->chain_vec == v && e->chain_block == blk &&
+               e->chain_stream == e->stream) ? 1 : 0;
+    a.publish = (o.pdl == 2) ? 1 : 0;
+    e->chain_ok = false;
+    CU(do_step(e, a, o, e->stream, false));
+    e->chain_ok = a.publish != 0; // a pdl == 2 step publishes its flags, chained or not
+    e->chain_vec = v;
+    e->chain_block = blk;
+    e->chain_stream = e->stream;
     after_step(e, step_flags, 1);
     return GYMRS_OK;
 }
@@ -555,6 +582,7 @@ int gymrs_step_host(gymrs_env *e, const void *actions, uint32_t step_flags,
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     CU(cudaSetDevice(e->device));
     if (!e->d_actions) CU(cudaMalloc(&e->d_actions, 4 * e->ld));
+    e->chain_ok = false; // the slice launches below use their own CTA numbering
     // Chunked three-stage pipeline: H2D(actions) -> step -> D2H(results), chunk c+1's copy-in
     // and chunk c-1's copy-out overlap chunk c's kernel.  Chunk boundaries are multiples of
     // 1024 envs so every chunk keeps the 128-bit access path.
@@ -608,6 +636,7 @@ int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t 
     a.obs_out = obs_out;
     a.reward_out = reward_out;
     a.done_out = done_out;
+    e->chain_ok = false;
     CU(do_step(e, a, make_opts(e, step_flags), e->stream, true));
     after_step(e, step_flags, n_steps);
     return GYMRS_OK;
@@ -631,6 +660,7 @@ int gymrs_set_state(gymrs_env *e, const float *state, const int32_t *sbt)
 {
     if (!e || !state) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     CU(cudaSetDevice(e->device));
+    e->chain_ok = false;
     CU(cudaMemcpy2DAsync(e->state, sizeof(float) * e->ld, state, sizeof(float) * e->n,
                          sizeof(float) * e->n, e->state_dim, cudaMemcpyHostToDevice, e->stream));
     if (e->sbt) {
@@ -727,6 +757,12 @@ int gymrs_sync(gymrs_env *e, uint64_t *bad_env)
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
+    if (e->err_host[3]) {
+        e->err_host[3] = 0;
+        e->chain_ok = false;
+        CU(cudaMemsetAsync(e->chain_mem, 0, sizeof(uint32_t), e->stream));
+        return fail(GYMRS_ERR_CUDA, "chained step launch timed out waiting for the previous step (pdl = 2 protocol error)");
+    }
     if (e->err_host[0]) {
         const uint64_t gid = (uint64_t)e->err_host[1] | ((uint64_t)e->err_host[2] << 32);
         if (bad_env) *bad_env = gid;

@@ -28,6 +28,34 @@ struct ResetBox {
     float cap[4];   // largest float below high
 };
 
+// num / den as MUFU.RCP plus one Newton correction on the quotient (4 instructions, result
+// within 1 ulp for normal operands) instead of the ~10-instruction IEEE division sequence with
+// its slow-path call.  A zero / non-finite den yields inf or NaN (never a finite wrong value).
+__device__ __forceinline__ float div_newton(float num, float den)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+    const float q = num * r;
+    return fmaf(fmaf(-den, q, num), r, q);
+}
+
+// sin and cos of a pole angle.  A live CartPole has |theta| <= 0.21 (+ one step), so the common
+// case needs neither range reduction nor quadrant selection: two short minimax polynomials on
+// [-pi/4, pi/4] (Cephes sinf/cosf coefficients, <= 1 ulp there).  Anything larger (a pole that
+// keeps falling when the caller never resets) takes the full-range sincosf.
+__device__ __forceinline__ void sincos_small(float x, float &s, float &c)
+{
+    if (fabsf(x) <= 0.78539816f) {
+        const float z = x * x;
+        const float ps = fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
+        const float pc = fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f);
+        s = fmaf(x * z, ps, x);
+        c = fmaf(z * z, pc, fmaf(z, -0.5f, 1.0f));
+    } else {
+        sincosf(x, &s, &c);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // CartPole -- reference: src/envs/classical_control/cartpole.rs:398-483
 // ---------------------------------------------------------------------------
@@ -61,13 +89,13 @@ struct CartPole {
         const float x = s[0], x_dot = s[1], theta = s[2], theta_dot = s[3];
         const float f = (a == 1) ? p.force_over_m : -p.force_over_m; // :414-418, already / M
         float sn, cs;
-        sincosf(theta, &sn, &cs); // :420-421 (IEEE-accurate path, never __sinf)
+        sincos_small(theta, sn, cs); // :420-421 (polynomial / sincosf, never the MUFU __sinf)
         // temp = (force + PML * theta_dot^2 * sin) / M                               :423-424
         const float temp = fmaf(p.pml_over_m * (theta_dot * theta_dot), sn, f);
         // thetaacc = (g sin - cos temp) / (l (4/3 - mp cos^2 / M))                   :425-428
         const float num = fmaf(p.gravity, sn, -(cs * temp));
         const float den = fmaf(-p.den_b, cs * cs, p.den_a);
-        const float thetaacc = num / den;
+        const float thetaacc = div_newton(num, den);
         // xacc = temp - PML thetaacc cos / M                                         :429
         const float xacc = fmaf(-(p.pml_over_m * thetaacc), cs, temp);
         float nx, nxd, nth, nthd;
@@ -84,7 +112,8 @@ struct CartPole {
         }
         s[0] = nx; s[1] = nxd; s[2] = nth; s[3] = nthd;
         // strict comparisons on the updated x, theta                                 :450-453
-        done = (nx < -p.x_thr) | (nx > p.x_thr) | (nth < -p.th_thr) | (nth > p.th_thr);
+        // (x < -T || x > T) == (|x| > T), NaN included (all false)
+        done = (fabsf(nx) > p.x_thr) | (fabsf(nth) > p.th_thr);
         reward = 1.0f;
     }
 

@@ -24,8 +24,14 @@ struct BatchArgs {
     uint64_t global_off; // global id of env 0
     uint64_t seed;       // Philox key
     uint64_t epoch;      // Philox counter high half for auto-resets in this step (rollout: first step)
-    uint32_t *err;       // device-visible words: [0] sticky flag, [1..2] one offending global id
-    int early_actions;   // step: read the action row before griddepcontrol.wait (LaunchOpts::pdl == 2)
+    uint32_t *err;       // device-visible words: [0] invalid-action flag, [1..2] one offending global id,
+                         // [3] chained-dependency timeout flag
+    int early_actions;   // step: read the action row before any dependency is resolved (LaunchOpts::pdl == 2)
+    // chained launches: per-CTA progress flags of this handle (see kernels_impl.cuh)
+    uint32_t *chain_flags; // [number of CTAs]; CTA b stores chain_seq here when its stores are done
+    uint32_t chain_seq;    // sequence number of this step (previous step of the handle = chain_seq - 1)
+    int chain;             // 1: wait on chain_flags[blockIdx.x] instead of the whole previous grid
+    int publish;           // 1: store chain_seq to chain_flags[blockIdx.x] at the end (pdl == 2 only)
     // rollout only
     uint32_t n_steps;
     uint64_t act_ld;     // row stride of actions
@@ -43,6 +49,36 @@ struct LaunchOpts {
     int vec;          // envs per thread: 1, 2 or 4 (0 = pick)
     int block;        // threads per CTA (0 = default)
 };
+
+// ---- launch geometry (shared by the launchers and the host library, which needs to know
+// whether two consecutive steps of a handle use the same CTA -> env mapping) ----
+inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// widest V the pointers of this launch allow
+inline int pick_vec(const BatchArgs &a, int want, bool rollout)
+{
+    int v = (want == 1 || want == 2 || want == 4) ? want : 4;
+    while (v > 1) {
+        const size_t fa = 4 * v;
+        bool ok = aligned(a.state, fa) && (a.ld % v) == 0 && aligned(a.actions, fa) &&
+                  aligned(a.reward, fa) && aligned(a.done, v) &&
+                  (!a.obs || aligned(a.obs, fa)) && (!a.sbt || aligned(a.sbt, fa)) &&
+                  (!a.elapsed || (aligned(a.elapsed, fa) && aligned(a.truncated, v)));
+        if (rollout) {
+            ok = ok && (a.act_ld % v) == 0 && (a.out_ld % v) == 0 &&
+                 (!a.obs_out || aligned(a.obs_out, fa)) && (!a.reward_out || aligned(a.reward_out, fa)) &&
+                 (!a.done_out || aligned(a.done_out, v));
+        }
+        if (ok) break;
+        v >>= 1;
+    }
+    return v;
+}
+
+inline int pick_block(const LaunchOpts &o)
+{
+    return (o.block >= 32 && o.block <= 256 && o.block % 32 == 0) ? o.block : 256;
+}
 
 template <class E>
 cudaError_t launch_step(const typename E::P &p, const BatchArgs &a, const LaunchOpts &o, cudaStream_t s);

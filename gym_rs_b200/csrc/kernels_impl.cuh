@@ -1,0 +1,470 @@
+// kernels_impl.cuh -- sm_100a kernels of the batched classic-control step path (templates;
+// instantiated per env in kernels_cartpole.cu, kernels_mountain_car.cu, kernels_pendulum.cu).
+//
+// One thread owns V consecutive env instances (V = 4 by default: every SoA row is read and
+// written with one 128-bit access per thread, 512 contiguous bytes per warp; V = 1 is the literal
+// "one lane per env" mapping, used for unaligned caller buffers).  The path is an elementwise map
+// at ~0.9 flop/B, so there are no tensor cores here: the roofline is HBM bandwidth.
+//
+// Kernels
+//   step_kernel     one transition of every env (+ same-launch auto-reset)
+//                   reference: Env::step, cartpole.rs:398-483, mountain_car.rs:398-435
+//   rollout_kernel  n_steps transitions with the state held in registers; actions are
+//                   prefetched one step ahead, per-step results streamed out
+//   reset_kernel    Env::reset, cartpole.rs:485-516, mountain_car.rs:464-501
+//
+// Launch-to-launch pipelining (step_kernel).  A 1M-env step moves only ~43 MB, i.e. ~6.5 us of
+// HBM time, so the ramp-up / drain of a stand-alone launch (~3 us) is a large fraction of it.
+// Steps are therefore launched with programmatic dependent launch (PDL) and, in chained mode,
+// do NOT wait for the whole previous grid: env i of step t+1 depends only on env i of step t,
+// which the CTA with the same index wrote.  Each CTA publishes a per-handle flag (release) when
+// its stores are done and the same-index CTA of the next step acquires it before loading.
+// Consecutive steps then overlap like one continuous stream of CTAs.  Deadlock-free because a
+// dependent grid is only launched once every CTA of its predecessor has started.
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "kernels.hpp"
+
+namespace gymrs {
+
+namespace {
+
+// ---- programmatic dependent launch (PDL) ----------------------------------
+// wait: block until the previous grid in the stream has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- V-wide row access ------------------------------------------------------
+template <int V> struct Pack;
+template <> struct Pack<1> { using F = float;  using I = int32_t; using B = uint8_t; using U = uint32_t; };
+template <> struct Pack<2> { using F = float2; using I = int2;    using B = uchar2;  using U = uint2; };
+template <> struct Pack<4> { using F = float4; using I = int4;    using B = uchar4;  using U = uint4; };
+template <int V, class T> struct PackOf;
+template <int V> struct PackOf<V, float>    { using type = typename Pack<V>::F; };
+template <int V> struct PackOf<V, int32_t>  { using type = typename Pack<V>::I; };
+template <int V> struct PackOf<V, uint32_t> { using type = typename Pack<V>::U; };
+template <int V> struct PackOf<V, uint8_t>  { using type = typename Pack<V>::B; };
+
+template <int V, class T, class PK>
+__device__ __forceinline__ void unpack(const PK &v, T (&r)[V])
+{
+    static_assert(sizeof(PK) == sizeof(T) * V, "pack size");
+    const T *e = reinterpret_cast<const T *>(&v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) r[j] = e[j];
+}
+template <int V, class T, class PK>
+__device__ __forceinline__ PK pack(const T (&r)[V])
+{
+    PK v;
+    T *e = reinterpret_cast<T *>(&v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) e[j] = r[j];
+    return v;
+}
+
+// FULL: all V elements are in range -> one vector access; otherwise guarded scalar accesses
+// (only the single ragged group at the end of a batch takes that path).
+//
+// Row loads use ld.global.cg (L2 only): every line is touched once per step, and bypassing the
+// non-coherent L1 keeps chained launches from ever seeing a stale line.
+template <int V, bool FULL, class T>
+__device__ __forceinline__ void ld_row(const T *p, T (&r)[V], int nvalid, T fill)
+{
+    if (FULL) {
+        using PK = typename PackOf<V, T>::type;
+        unpack<V>(__ldcg(reinterpret_cast<const PK *>(p)), r);
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) r[j] = (j < nvalid) ? __ldcg(p + j) : fill;
+    }
+}
+// read-only streaming load (actions are consumed once): ld.global.nc
+template <int V, bool FULL, class T>
+__device__ __forceinline__ void ld_stream(const T *p, T (&r)[V], int nvalid)
+{
+    static_assert(sizeof(T) == 4, "4-byte actions");
+    if (FULL) {
+        unpack<V>(__ldg(reinterpret_cast<const typename Pack<V>::U *>(p)), r);
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) r[j] = (j < nvalid) ? __ldg(p + j) : T(0);
+    }
+}
+// STREAM: st.global.cs (evict-first) for outputs nobody re-reads on the device
+template <int V, bool FULL, bool STREAM = false, class T>
+__device__ __forceinline__ void st_row(T *p, const T (&r)[V], int nvalid)
+{
+    if (FULL) {
+        using PK = typename PackOf<V, T>::type;
+        if (STREAM) __stcs(reinterpret_cast<PK *>(p), pack<V, T, PK>(r));
+        else *reinterpret_cast<PK *>(p) = pack<V, T, PK>(r);
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) if (j < nvalid) p[j] = r[j];
+    }
+}
+
+__device__ __forceinline__ void report_invalid(uint32_t *err, uint64_t gid)
+{
+    // sticky; any one offender is reported (the reference panics on the first it meets)
+    err[1] = (uint32_t)gid;
+    err[2] = (uint32_t)(gid >> 32);
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(err) = 1u;
+}
+
+// ---- one transition of the V envs a thread owns, all on registers ------------
+template <class E, int V, bool AR, bool SBT, bool TL>
+__device__ __forceinline__ void transition(const typename E::P &p, const BatchArgs &a,
+                                           float (&s)[E::SD][V], float (&o)[E::OD][V],
+                                           const typename E::Action (&act)[V],
+                                           int32_t (&sbt)[V], uint32_t (&el)[V],
+                                           float (&rew)[V], uint8_t (&dn)[V], uint8_t (&tr)[V],
+                                           uint64_t gid0, uint64_t epoch, int nvalid)
+{
+    uint32_t need_reset = 0; // bit j: env j of this thread ended its episode in this step
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        float sj[E::SD], oj[E::OD];
+#pragma unroll
+        for (int r = 0; r < E::SD; ++r) sj[r] = s[r][j];
+#pragma unroll
+        for (int r = 0; r < E::OD; ++r) oj[r] = o[r][j];
+        float reward = 0.0f;
+        bool done = false, trunc = false;
+        if (E::valid(act[j])) {
+            E::step(p, sj, act[j], oj, reward, done);
+            if (SBT && E::HAS_SBT) {
+                // reward 1.0 while alive and on the FIRST terminal step, 0.0 afterwards
+                // (cartpole.rs:455-464); the state keeps integrating.
+                if (done) {
+                    if (sbt[j] < 0) { sbt[j] = 0; }
+                    else { sbt[j] += 1; reward = 0.0f; }
+                }
+            }
+            if (TL) {
+                el[j] += 1u;
+                trunc = el[j] >= a.max_steps;
+            }
+            if (AR && (done || trunc)) need_reset |= 1u << j;
+        } else if (j < nvalid) {
+            report_invalid(a.err, gid0 + j); //                            cartpole.rs:402-406
+        }
+#pragma unroll
+        for (int r = 0; r < E::SD; ++r) s[r][j] = sj[r];
+#pragma unroll
+        for (int r = 0; r < E::OD; ++r) o[r][j] = oj[r];
+        rew[j] = reward;
+        dn[j] = done ? 1 : 0;
+        tr[j] = trunc ? 1 : 0;
+    }
+    if (AR) {
+        // Same-launch auto-reset (examples/cartpole.rs:23-28 does it by hand).  Only a few percent
+        // of envs end per step, so instead of a predicated Philox per slot (which nearly every warp
+        // would execute V times) each thread draws once per finished env: the loop runs as often as
+        // the busiest lane of the warp needs, typically once.
+        while (need_reset) {
+            const int j = __ffs(need_reset) - 1;
+            need_reset &= need_reset - 1;
+            float sj[E::SD], oj[E::OD];
+            E::reset(p, sj, oj, reset_words(a.seed, gid0 + j, epoch));
+#pragma unroll
+            for (int jj = 0; jj < V; ++jj) {
+                if (jj == j) {
+#pragma unroll
+                    for (int r = 0; r < E::SD; ++r) s[r][jj] = sj[r];
+                    if (!E::OBS_IS_STATE) {
+#pragma unroll
+                        for (int r = 0; r < E::OD; ++r) o[r][jj] = oj[r];
+                    }
+                    if (SBT) sbt[jj] = -1; //                              cartpole.rs:504
+                    if (TL) el[jj] = 0u;
+                }
+            }
+        }
+    }
+}
+
+// ---- step -------------------------------------------------------------------
+#ifndef GYMRS_STEP_MIN_CTAS
+#define GYMRS_STEP_MIN_CTAS 5 // <= 51 registers/thread: 5 CTAs of 256 threads resident per SM
+#endif
+
+template <class E, int V, bool AR, bool SBT, bool TL, bool FULL>
+__device__ __forceinline__ void step_body(const typename E::P &p, const BatchArgs &a, uint64_t i0,
+                                          int nvalid, typename E::Action (&act)[V])
+{
+    float s[E::SD][V], o[E::OD][V];
+#pragma unroll
+    for (int r = 0; r < E::SD; ++r) ld_row<V, FULL>(a.state + r * a.ld + i0, s[r], nvalid, 0.0f);
+    int32_t sbt[V];
+    uint32_t el[V];
+    if (SBT) ld_row<V, FULL>(a.sbt + i0, sbt, nvalid, int32_t(-1));
+    if (TL) ld_row<V, FULL>(a.elapsed + i0, el, nvalid, uint32_t(0));
+
+    float rew[V];
+    uint8_t dn[V], tr[V];
+    transition<E, V, AR, SBT, TL>(p, a, s, o, act, sbt, el, rew, dn, tr, a.global_off + i0, a.epoch, nvalid);
+
+#pragma unroll
+    for (int r = 0; r < E::SD; ++r) st_row<V, FULL>(a.state + r * a.ld + i0, s[r], nvalid);
+    if (!E::OBS_IS_STATE) {
+#pragma unroll
+        for (int r = 0; r < E::OD; ++r) st_row<V, FULL>(a.obs + r * a.ld + i0, o[r], nvalid);
+    }
+    st_row<V, FULL>(a.reward + i0, rew, nvalid);
+    st_row<V, FULL>(a.done + i0, dn, nvalid);
+    if (TL) st_row<V, FULL>(a.truncated + i0, tr, nvalid);
+    if (SBT) st_row<V, FULL>(a.sbt + i0, sbt, nvalid);
+    if (TL) st_row<V, FULL>(a.elapsed + i0, el, nvalid);
+}
+
+template <class E, int V, bool AR, bool SBT, bool TL>
+__global__ void __launch_bounds__(256, GYMRS_STEP_MIN_CTAS)
+step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ BatchArgs a)
+{
+    using A = typename E::Action;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    const bool live = i0 < a.n;
+    const bool full = i0 + V <= a.n;
+    const int nvalid = live ? (full ? V : (int)(a.n - i0)) : 0;
+    const A *actp = reinterpret_cast<const A *>(a.actions) + i0;
+
+    A act[V];
+    // pdl == 2: the caller guarantees the action batch predates the previous launch, so it can
+    // be fetched before any dependency is resolved
+    if (a.early_actions) {
+        if (full) ld_stream<V, true>(actp, act, nvalid);
+        else if (live) ld_stream<V, false>(actp, act, nvalid);
+    }
+
+    // let the next launch in the stream get its CTAs scheduled as soon as SM slots free up
+    pdl_launch_dependents();
+
+    if (a.chain) {
+        // fine-grained dependency: these envs were last written by CTA blockIdx.x of the previous
+        // step of this handle; wait for that CTA only, not for the whole previous grid
+        if (threadIdx.x == 0) {
+            const uint32_t want = a.chain_seq - 1u;
+            // chain_flags[-1] is the handle's "protocol broken" word: once any CTA has timed out,
+            // nobody spins again (a bug must surface as an error code, never as a hung device)
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(a.chain_flags + blockIdx.x) != want) {
+                __nanosleep(32);
+                if ((++spins & 1023u) == 0 && (spins > (1u << 17) || ld_acquire_gpu(a.chain_flags - 1) != 0u)) {
+                    st_release_gpu(a.chain_flags - 1, 1u);
+                    *reinterpret_cast<volatile uint32_t *>(a.err + 3) = 1u;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    } else {
+        // touch nothing the previous launch writes until it has completed and flushed
+        pdl_wait();
+    }
+
+    if (live) {
+        if (!a.early_actions) {
+            if (full) ld_stream<V, true>(actp, act, nvalid);
+            else ld_stream<V, false>(actp, act, nvalid);
+        }
+        if (full) step_body<E, V, AR, SBT, TL, true>(p, a, i0, nvalid, act);
+        else step_body<E, V, AR, SBT, TL, false>(p, a, i0, nvalid, act);
+    }
+
+    // publish "this CTA's envs are at step chain_seq" for the next chained launch.  The barrier
+    // orders every thread's stores before thread 0's release (cumulativity), so one release store
+    // per CTA is enough.  Skipped entirely outside pdl == 2 so plain launches pay nothing.
+    if (a.publish) {
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu(a.chain_flags + blockIdx.x, a.chain_seq);
+    }
+}
+
+// ---- fused rollout ------------------------------------------------------------
+// n_steps transitions in one launch.  State lives in registers; per step the kernel
+// reads one action row and streams out observation / reward / done.  The actions of
+// step k+1 are loaded before the math of step k so their latency is covered.
+template <class E, int V, bool AR, bool SBT, bool TL, bool FULL>
+__device__ __forceinline__ void rollout_body(const typename E::P &p, const BatchArgs &a, uint64_t i0, int nvalid)
+{
+    using A = typename E::Action;
+    const A *actp = reinterpret_cast<const A *>(a.actions) + i0;
+    A act[V], act_next[V];
+    ld_stream<V, FULL>(actp, act, nvalid);
+
+    float s[E::SD][V], o[E::OD][V];
+#pragma unroll
+    for (int r = 0; r < E::SD; ++r) ld_row<V, FULL>(a.state + r * a.ld + i0, s[r], nvalid, 0.0f);
+    int32_t sbt[V];
+    uint32_t el[V];
+    if (SBT) ld_row<V, FULL>(a.sbt + i0, sbt, nvalid, int32_t(-1));
+    if (TL) ld_row<V, FULL>(a.elapsed + i0, el, nvalid, uint32_t(0));
+    float rew[V];
+    uint8_t dn[V], tr[V];
+
+    for (uint32_t k = 0; k < a.n_steps; ++k) {
+        if (k + 1 < a.n_steps) ld_stream<V, FULL>(actp + (uint64_t)(k + 1) * a.act_ld, act_next, nvalid);
+        transition<E, V, AR, SBT, TL>(p, a, s, o, act, sbt, el, rew, dn, tr, a.global_off + i0,
+                                      a.epoch + k, nvalid);
+        if (a.obs_out) {
+            float *ob = a.obs_out + (uint64_t)k * E::OD * a.out_ld + i0;
+#pragma unroll
+            for (int r = 0; r < E::OD; ++r) {
+                if constexpr (E::OBS_IS_STATE) st_row<V, FULL, true>(ob + r * a.out_ld, s[r], nvalid);
+                else st_row<V, FULL, true>(ob + r * a.out_ld, o[r], nvalid);
+            }
+        }
+        if (a.reward_out) st_row<V, FULL, true>(a.reward_out + (uint64_t)k * a.out_ld + i0, rew, nvalid);
+        if (a.done_out) st_row<V, FULL, true>(a.done_out + (uint64_t)k * a.out_ld + i0, dn, nvalid);
+#pragma unroll
+        for (int j = 0; j < V; ++j) act[j] = act_next[j];
+    }
+
+#pragma unroll
+    for (int r = 0; r < E::SD; ++r) st_row<V, FULL>(a.state + r * a.ld + i0, s[r], nvalid);
+    if (!E::OBS_IS_STATE) {
+#pragma unroll
+        for (int r = 0; r < E::OD; ++r) st_row<V, FULL>(a.obs + r * a.ld + i0, o[r], nvalid);
+    }
+    st_row<V, FULL>(a.reward + i0, rew, nvalid);
+    st_row<V, FULL>(a.done + i0, dn, nvalid);
+    if (TL) st_row<V, FULL>(a.truncated + i0, tr, nvalid);
+    if (SBT) st_row<V, FULL>(a.sbt + i0, sbt, nvalid);
+    if (TL) st_row<V, FULL>(a.elapsed + i0, el, nvalid);
+}
+
+template <class E, int V, bool AR, bool SBT, bool TL>
+__global__ void __launch_bounds__(256)
+rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ BatchArgs a)
+{
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    if (i0 >= a.n) return;
+    if (i0 + V <= a.n) rollout_body<E, V, AR, SBT, TL, true>(p, a, i0, V);
+    else rollout_body<E, V, AR, SBT, TL, false>(p, a, i0, (int)(a.n - i0));
+}
+
+// ---- reset ----------------------------------------------------------------------
+template <class E>
+__global__ void __launch_bounds__(256)
+reset_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ BatchArgs a,
+             const uint8_t *__restrict__ mask)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    if (mask && !mask[i]) return;
+    float s[E::SD], o[E::OD];
+    E::reset(p, s, o, reset_words(a.seed, a.global_off + i, 0));
+#pragma unroll
+    for (int r = 0; r < E::SD; ++r) a.state[r * a.ld + i] = s[r];
+    if (!E::OBS_IS_STATE) {
+#pragma unroll
+        for (int r = 0; r < E::OD; ++r) a.obs[r * a.ld + i] = o[r];
+    }
+    a.reward[i] = 0.0f;
+    a.done[i] = 0;
+    if (a.sbt) a.sbt[i] = -1; //              cartpole.rs:504
+    if (a.elapsed) { a.elapsed[i] = 0u; a.truncated[i] = 0; }
+}
+
+// ---- launch helpers ----------------------------------------------------------------
+template <class K, class P>
+cudaError_t launch_ex(K kernel, uint64_t threads, int block, bool pdl, cudaStream_t s,
+                      const P &p, BatchArgs a)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((threads + block - 1) / block));
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (!pdl) { a.early_actions = 0; a.chain = 0; }
+    return cudaLaunchKernelEx(&cfg, kernel, p, a);
+}
+
+template <class E, int V, bool ROLLOUT>
+cudaError_t dispatch_flags(const typename E::P &p, const BatchArgs &a_in, const LaunchOpts &o, cudaStream_t s)
+{
+    const uint64_t threads = (a_in.n + V - 1) / V;
+    const int block = pick_block(o);
+    const bool sbt = E::HAS_SBT && o.use_sbt;
+    BatchArgs a = a_in;
+    a.early_actions = (o.pdl == 2);
+    const int key = (o.autoreset ? 4 : 0) | (sbt ? 2 : 0) | (o.time_limit ? 1 : 0);
+#define GYMRS_CASE(K, AR, SB, TL)                                                                   \
+    case K:                                                                                         \
+        return ROLLOUT ? launch_ex(rollout_kernel<E, V, AR, SB, TL>, threads, block, false, s, p, a) \
+                       : launch_ex(step_kernel<E, V, AR, SB, TL>, threads, block, o.pdl != 0, s, p, a);
+    switch (key) {
+        GYMRS_CASE(0, false, false, false)
+        GYMRS_CASE(1, false, false, true)
+        GYMRS_CASE(2, false, true, false)
+        GYMRS_CASE(3, false, true, true)
+        GYMRS_CASE(4, true, false, false)
+        GYMRS_CASE(5, true, false, true)
+        GYMRS_CASE(6, true, true, false)
+        GYMRS_CASE(7, true, true, true)
+    }
+#undef GYMRS_CASE
+    return cudaErrorInvalidValue;
+}
+
+template <class E, bool ROLLOUT>
+cudaError_t dispatch_vec(const typename E::P &p, const BatchArgs &a, const LaunchOpts &o, cudaStream_t s)
+{
+    if (a.n == 0) return cudaSuccess;
+    switch (pick_vec(a, o.vec, ROLLOUT)) {
+    case 4: return dispatch_flags<E, 4, ROLLOUT>(p, a, o, s);
+    case 2: return dispatch_flags<E, 2, ROLLOUT>(p, a, o, s);
+    default: return dispatch_flags<E, 1, ROLLOUT>(p, a, o, s);
+    }
+}
+
+} // namespace
+
+template <class E>
+cudaError_t launch_step(const typename E::P &p, const BatchArgs &a, const LaunchOpts &o, cudaStream_t s)
+{
+    return dispatch_vec<E, false>(p, a, o, s);
+}
+
+template <class E>
+cudaError_t launch_rollout(const typename E::P &p, const BatchArgs &a, const LaunchOpts &o, cudaStream_t s)
+{
+    return dispatch_vec<E, true>(p, a, o, s);
+}
+
+template <class E>
+cudaError_t launch_reset(const typename E::P &p, const BatchArgs &a, const uint8_t *mask, cudaStream_t s)
+{
+    if (a.n == 0) return cudaSuccess;
+    reset_kernel<E><<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(p, a, mask);
+    return cudaGetLastError();
+}
+
+// Each env is instantiated in its own translation unit (kernels_<env>.cu) so the three compile
+// in parallel.
+#define GYMRS_INSTANTIATE(E)                                                                              \
+    template cudaError_t launch_step<E>(const E::P &, const BatchArgs &, const LaunchOpts &, cudaStream_t);   \
+    template cudaError_t launch_rollout<E>(const E::P &, const BatchArgs &, const LaunchOpts &, cudaStream_t); \
+    template cudaError_t launch_reset<E>(const E::P &, const BatchArgs &, const uint8_t *, cudaStream_t);
+
+} // namespace gymrs

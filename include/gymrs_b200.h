@@ -185,11 +185,16 @@ int gymrs_sync(gymrs_env *env, uint64_t *bad_env);
 /* Launch tuning (not part of the reference surface).
  * vec: env instances per thread, 0 = widest the buffer alignment allows (4), or 1 / 2 / 4.
  * block: threads per CTA, 0 = 256.
- * pdl: 0 = plain stream order; 1 (default) = programmatic dependent launch, the next step's
- *      CTAs are scheduled while the previous step drains but touch memory only after it has
- *      completed; 2 = as 1 and the action batch is read BEFORE that wait -- only valid when
- *      the action buffer was complete before the previous launch in the stream started
- *      (pre-generated rollouts), never when a policy kernel writes it just before the step. */
+ * pdl: 0 = plain stream order.
+ *      1 (default) = programmatic dependent launch: the next step's CTAs are scheduled while the
+ *        previous launch drains, but touch memory only after it has completed.
+ *      2 = pipelined rollouts: back-to-back gymrs_step calls overlap.  A step reads its action
+ *        batch immediately and waits, per CTA, only for the CTA of the handle's previous step that
+ *        wrote the same env instances (per-handle progress flags), not for the whole previous
+ *        launch.  Only valid when the action batch was complete before the PREVIOUS launch on the
+ *        stream started (pre-generated rollouts): a kernel that writes the actions right before
+ *        the step is not ordered before it.  Every other gymrs_* call on the handle, and every
+ *        non-kernel operation on the stream, still acts as a full barrier. */
 int gymrs_set_launch_config(gymrs_env *env, int vec, int block, int pdl);
 
 /* Pinned host memory for the *_host entry points. */

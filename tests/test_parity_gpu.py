@@ -476,6 +476,44 @@ def test_vec_widths_and_ragged_sizes_are_bit_identical(torch, g, kind):
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("kind,n,vec,block", [("cartpole", N_FULL, 0, 0), ("cartpole", 300001, 1, 32),
+                                              ("mountain_car", 1 << 19, 2, 64), ("pendulum", 777777, 4, 128)])
+def test_chained_pdl_launches_match_plain_launches(torch, g, kind, n, vec, block):
+    """pdl = 2 pipelines back-to-back steps: a CTA waits only for the same-index CTA of the handle's
+    previous step (per-CTA release/acquire flags) instead of the whole previous grid.  Results must
+    be bit-identical to plain stream-ordered launches, also when several handles interleave on one
+    stream and when other calls (reset, set_state, rollout, host step) break the chain."""
+    cls = {"cartpole": g.CartPoleEnv, "mountain_car": g.MountainCarEnv, "pendulum": g.PendulumEnv}[kind]
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    if kind == "pendulum":
+        acts = [torch.rand((n,), generator=gen, device="cuda") * 4 - 2 for _ in range(8)]
+    else:
+        acts = [torch.randint(0, 2, (n,), generator=gen, device="cuda", dtype=torch.int32) for _ in range(8)]
+    torch.cuda.synchronize()
+    finals = {}
+    for pdl in (0, 2):
+        envs = [cls(num_envs=n, global_env_offset=k * n) for k in range(3)]
+        for e in envs:
+            e.set_launch_config(vec=vec, block=block, pdl=pdl)
+            e.reset(seed=11)
+        for t in range(240):
+            for k, e in enumerate(envs):  # three handles interleaved on one stream
+                e.step(acts[(t + k) % 8], autoreset=True)
+            if t == 100:   # chain breakers in the middle of the run
+                st = envs[0].get_state()
+                envs[0].set_state(st)
+                envs[1].reset(seed=5)
+                envs[2].rollout(torch.stack(acts[:2]), autoreset=True)
+        for e in envs:
+            e.sync()
+        finals[pdl] = [(e.get_state(), e._t_reward.cpu().numpy(), e._t_done.cpu().numpy()) for e in envs]
+        for e in envs:
+            e.close()
+    for a, b in zip(finals[0], finals[2]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
 def test_unaligned_action_pointer_falls_back_to_scalar_lanes(torch, g):
     n = 8192
     st, act = cartpole_inputs(n + 1, seed=8)
