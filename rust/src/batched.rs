@@ -1,0 +1,104 @@
+//! N env instances per handle: the shape the GPU path is built for.  `ActionReward` carries a scalar
+//! reward/done (core.rs:94-106), so the batched surface returns SoA slices instead.
+use std::os::raw::c_void;
+
+use crate::ffi;
+
+/// Which environment a [`BatchedEnv`] holds.
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+pub enum Kind {
+    CartPole,
+    MountainCar,
+    Pendulum,
+}
+
+/// Host-side view of one batched step: `observation[k * num_envs + i]` is field k of env i.
+pub struct BatchStep<'a> {
+    pub observation: &'a [f32],
+    pub reward: &'a [f32],
+    pub done: &'a [u8],
+    pub truncated: &'a [u8],
+}
+
+pub struct BatchedEnv {
+    handle: *mut ffi::gymrs_env,
+    num_envs: usize,
+    obs_dim: usize,
+    actions: Vec<i32>,
+    obs: Vec<f32>,
+    reward: Vec<f32>,
+    done: Vec<u8>,
+    truncated: Vec<u8>,
+}
+
+impl BatchedEnv {
+    /// `global_env_offset` keys the reset RNG, so shards of one logical batch on several GPUs give
+    /// the same per-env results as a single handle.
+    pub fn new(kind: Kind, num_envs: usize, device: i32, global_env_offset: u64) -> Self {
+        let k = match kind {
+            Kind::CartPole => ffi::GYMRS_CARTPOLE,
+            Kind::MountainCar => ffi::GYMRS_MOUNTAIN_CAR,
+            Kind::Pendulum => ffi::GYMRS_PENDULUM,
+        };
+        let mut handle = std::ptr::null_mut();
+        unsafe {
+            ffi::check(ffi::gymrs_create(k, num_envs as u64, device, global_env_offset, std::ptr::null(), 0, &mut handle));
+        }
+        let obs_dim = match kind { Kind::CartPole => 4, Kind::MountainCar => 2, Kind::Pendulum => 3 };
+        Self {
+            handle,
+            num_envs,
+            obs_dim,
+            actions: vec![0; num_envs],
+            obs: vec![0.0; obs_dim * num_envs],
+            reward: vec![0.0; num_envs],
+            done: vec![0; num_envs],
+            truncated: vec![0; num_envs],
+        }
+    }
+
+    pub fn reset(&mut self, seed: Option<u64>) -> u64 {
+        let mut used = 0u64;
+        let p = seed.as_ref().map_or(std::ptr::null(), |s| s as *const u64);
+        unsafe { ffi::check(ffi::gymrs_reset(self.handle, p, std::ptr::null(), std::ptr::null(), std::ptr::null(), &mut used)) };
+        used
+    }
+
+    /// Discrete envs.  Panics like the reference on an action outside the action space.
+    pub fn step(&mut self, actions: &[usize], autoreset: bool) -> BatchStep<'_> {
+        assert_eq!(actions.len(), self.num_envs);
+        for (d, a) in self.actions.iter_mut().zip(actions) {
+            *d = i32::try_from(*a).unwrap_or(i32::MAX); // out-of-range values are rejected on the device
+        }
+        let flags = if autoreset { ffi::GYMRS_STEP_AUTORESET } else { 0 };
+        unsafe {
+            ffi::check(ffi::gymrs_step_host(self.handle, self.actions.as_ptr() as *const c_void, flags,
+                                            self.obs.as_mut_ptr(), self.reward.as_mut_ptr(),
+                                            self.done.as_mut_ptr(), self.truncated.as_mut_ptr()));
+            let mut bad = 0u64;
+            let rc = ffi::gymrs_sync(self.handle, &mut bad);
+            if rc == ffi::GYMRS_ERR_INVALID_ACTION {
+                panic!("{} usize invalid", actions[(bad as usize) % self.num_envs]);
+            }
+            ffi::check(rc);
+        }
+        BatchStep { observation: &self.obs, reward: &self.reward, done: &self.done, truncated: &self.truncated }
+    }
+
+    pub fn num_envs(&self) -> usize {
+        self.num_envs
+    }
+    pub fn obs_dim(&self) -> usize {
+        self.obs_dim
+    }
+    /// Raw handle for callers that keep actions / results on the device (`gymrs_step`, `gymrs_rollout`).
+    pub fn raw(&self) -> *mut ffi::gymrs_env {
+        self.handle
+    }
+}
+
+impl Drop for BatchedEnv {
+    fn drop(&mut self) {
+        unsafe { ffi::gymrs_destroy(self.handle) };
+    }
+}

@@ -1,0 +1,110 @@
+//! Raw `extern "C"` declarations of `include/gymrs_b200.h` (ABI version 1).
+#![allow(non_camel_case_types, dead_code)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct gymrs_env {
+    _private: [u8; 0],
+}
+
+pub const GYMRS_CARTPOLE: c_int = 0;
+pub const GYMRS_MOUNTAIN_CAR: c_int = 1;
+pub const GYMRS_PENDULUM: c_int = 2;
+
+pub const GYMRS_OK: c_int = 0;
+pub const GYMRS_ERR_INVALID_ACTION: c_int = 1;
+
+pub const GYMRS_FLAG_TIME_LIMIT: u32 = 0x1;
+pub const GYMRS_STEP_AUTORESET: u32 = 0x1;
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct gymrs_cartpole_params {
+    pub gravity: f64,
+    pub masscart: f64,
+    pub masspole: f64,
+    pub length: f64,
+    pub force_mag: f64,
+    pub tau: f64,
+    pub theta_threshold_radians: f64,
+    pub x_threshold: f64,
+    pub kinematics_integrator: i32,
+    pub max_episode_steps: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct gymrs_mountain_car_params {
+    pub min_position: f64,
+    pub max_position: f64,
+    pub max_speed: f64,
+    pub goal_position: f64,
+    pub goal_velocity: f64,
+    pub force: f64,
+    pub gravity: f64,
+    pub max_episode_steps: i32,
+    pub _pad: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct gymrs_buffers {
+    pub num_envs: u64,
+    pub ld: u64,
+    pub state_dim: u32,
+    pub obs_dim: u32,
+    pub state: *mut f32,
+    pub obs: *mut f32,
+    pub reward: *mut f32,
+    pub done: *mut u8,
+    pub truncated: *mut u8,
+    pub steps_beyond_terminated: *mut i32,
+    pub elapsed_steps: *mut u32,
+}
+
+extern "C" {
+    pub fn gymrs_abi_version() -> c_int;
+    pub fn gymrs_last_error() -> *const c_char;
+    pub fn gymrs_device_count() -> c_int;
+    pub fn gymrs_default_params(kind: c_int, params: *mut c_void) -> c_int;
+    pub fn gymrs_create(kind: c_int, num_envs: u64, device: c_int, global_env_offset: u64,
+                        params: *const c_void, flags: u32, out: *mut *mut gymrs_env) -> c_int;
+    pub fn gymrs_destroy(env: *mut gymrs_env) -> c_int;
+    pub fn gymrs_clone(env: *const gymrs_env, out: *mut *mut gymrs_env) -> c_int;
+    pub fn gymrs_set_params(env: *mut gymrs_env, params: *const c_void) -> c_int;
+    pub fn gymrs_get_params(env: *const gymrs_env, params: *mut c_void) -> c_int;
+    pub fn gymrs_set_stream(env: *mut gymrs_env, cuda_stream: *mut c_void) -> c_int;
+    pub fn gymrs_get_stream(env: *const gymrs_env, cuda_stream: *mut *mut c_void) -> c_int;
+    pub fn gymrs_reset(env: *mut gymrs_env, seed: *const u64, low: *const f32, high: *const f32,
+                       mask: *const u8, seed_used: *mut u64) -> c_int;
+    pub fn gymrs_step(env: *mut gymrs_env, actions: *const c_void, step_flags: u32) -> c_int;
+    pub fn gymrs_step_host(env: *mut gymrs_env, actions: *const c_void, step_flags: u32, obs: *mut f32,
+                           reward: *mut f32, done: *mut u8, truncated: *mut u8) -> c_int;
+    pub fn gymrs_rollout(env: *mut gymrs_env, actions: *const c_void, n_steps: u32, step_flags: u32,
+                         obs_out: *mut f32, reward_out: *mut f32, done_out: *mut u8) -> c_int;
+    pub fn gymrs_get_state(env: *mut gymrs_env, state: *mut f32, sbt: *mut i32) -> c_int;
+    pub fn gymrs_set_state(env: *mut gymrs_env, state: *const f32, sbt: *const i32) -> c_int;
+    pub fn gymrs_get_buffers(env: *mut gymrs_env, out: *mut gymrs_buffers) -> c_int;
+    pub fn gymrs_action_space(env: *const gymrs_env, n: *mut u64, low: *mut f32, high: *mut f32) -> c_int;
+    pub fn gymrs_observation_space(env: *const gymrs_env, low: *mut f64, high: *mut f64) -> c_int;
+    pub fn gymrs_reward_range(env: *const gymrs_env, low: *mut f64, high: *mut f64) -> c_int;
+    pub fn gymrs_num_envs(env: *const gymrs_env, n: *mut u64) -> c_int;
+    pub fn gymrs_kind_of(env: *const gymrs_env, kind: *mut c_int) -> c_int;
+    pub fn gymrs_sync(env: *mut gymrs_env, bad_env: *mut u64) -> c_int;
+    pub fn gymrs_set_launch_config(env: *mut gymrs_env, vec: c_int, block: c_int, pdl: c_int) -> c_int;
+    pub fn gymrs_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn gymrs_host_free(p: *mut c_void) -> c_int;
+    pub fn gymrs_clip(value: f64, left_bound: f64, right_bound: f64) -> f64;
+    pub fn gymrs_discrete_contains(n: u64, value: u64) -> c_int;
+    pub fn gymrs_rand_random(seed: *const u64) -> u64;
+}
+
+/// Turns a non-zero status into a panic carrying the library's message: the reference's error
+/// model is `panic!`/`assert!`, never `Result` (cartpole.rs:402-406), and nothing unwinds across
+/// the FFI boundary itself.
+pub fn check(rc: c_int) {
+    if rc != GYMRS_OK {
+        let msg = unsafe { std::ffi::CStr::from_ptr(gymrs_last_error()) };
+        panic!("gymrs error {}: {}", rc, msg.to_string_lossy());
+    }
+}
