@@ -96,7 +96,7 @@ struct gymrs_env {
     uint32_t *chain_mem = nullptr;
     uint32_t chain_seq = 0;         // sequence number of the last step launched on this handle
     bool chain_ok = false;          // flags describe the handle's current state for (chain_vec, chain_block)
-    int chain_vec = 0, chain_block = 0;
+    int chain_flag_envs = 0;        // env instances per flag of the launch that wrote the flags
     cudaStream_t chain_stream = nullptr;
 
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -506,7 +506,7 @@ int gymrs_get_stream(const gymrs_env *e, void **cuda_stream)
 int gymrs_set_launch_config(gymrs_env *e, int vec, int block, int pdl)
 {
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
-    if (!(vec == 0 || vec == 1 || vec == 2 || vec == 4)) return fail(GYMRS_ERR_BAD_ARG, "vec must be 0, 1, 2 or 4");
+    if (!(vec == 0 || vec == 1 || vec == 2 || vec == 4 || vec == 8)) return fail(GYMRS_ERR_BAD_ARG, "vec must be 0, 1, 2, 4 or 8");
     if (block != 0 && (block < 32 || block > 256 || block % 32)) return fail(GYMRS_ERR_BAD_ARG, "block must be a multiple of 32 in [32, 256]");
     if (pdl < 0 || pdl > 2) return fail(GYMRS_ERR_BAD_ARG, "pdl must be 0, 1 or 2");
     e->vec = vec; e->block = block; e->pdl = pdl;
@@ -561,16 +561,14 @@ int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
     const LaunchOpts o = make_opts(e, step_flags);
     // Chained launch: this step may skip the grid-wide dependency on the previous launch when the
     // handle's per-CTA flags describe its current state for exactly this CTA -> env mapping.
-    const int v = pick_vec(a, o.vec, false), blk = pick_block(o);
+    const int fe = (int)flag_envs(a, o);
     a.chain_seq = ++e->chain_seq;
-    a.chain = (o.pdl == 2 && e->chain_ok && e->chain_vec == v && e->chain_block == blk &&
-               e->chain_stream == e->stream) ? 1 : 0;
+    a.chain = (o.pdl == 2 && e->chain_ok && e->chain_flag_envs == fe && e->chain_stream == e->stream) ? 1 : 0;
     a.publish = (o.pdl == 2) ? 1 : 0;
     e->chain_ok = false;
     CU(do_step(e, a, o, e->stream, false));
     e->chain_ok = a.publish != 0; // a pdl == 2 step publishes its flags, chained or not
-    e->chain_vec = v;
-    e->chain_block = blk;
+    e->chain_flag_envs = fe;
     e->chain_stream = e->stream;
     after_step(e, step_flags, 1);
     return GYMRS_OK;

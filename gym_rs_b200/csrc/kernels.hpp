@@ -1,6 +1,8 @@
 // kernels.hpp -- host-visible launch interface of kernels.cu.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
+#include <string>
 #include <cuda_runtime.h>
 
 #include "envs.cuh"
@@ -46,7 +48,7 @@ struct LaunchOpts {
     bool use_sbt;     // CartPole: read/update steps_beyond_terminated
     bool time_limit;
     int pdl;          // 0 off; 1 programmatic dependent launch; 2 = 1 + actions read before the dependency wait
-    int vec;          // envs per thread: 1, 2 or 4 (0 = pick)
+    int vec;          // envs per thread: 1, 2 or 4 (0 = pick); 8 = persistent TMA-staged kernel
     int block;        // threads per CTA (0 = default)
 };
 
@@ -78,6 +80,21 @@ inline int pick_vec(const BatchArgs &a, int want, bool rollout)
 inline int pick_block(const LaunchOpts &o)
 {
     return (o.block >= 32 && o.block <= 256 && o.block % 32 == 0) ? o.block : 256;
+}
+
+// The persistent TMA-staged step kernel (step_stream_kernel) is opt-in: vec = 8 in the launch
+// config.  It needs every row to allow 128-bit access and a whole number of 4-env groups;
+// otherwise the launch silently uses step_kernel.
+inline bool use_tma_step(const BatchArgs &a, const LaunchOpts &o)
+{
+    return o.vec == 8 && (o.block == 0 || o.block == 256) && (a.n % 4) == 0 && pick_vec(a, 0, false) == 4;
+}
+
+// env instances covered by one chained-launch progress flag for this launch
+inline uint32_t flag_envs(const BatchArgs &a, const LaunchOpts &o)
+{
+    if (use_tma_step(a, o)) return 1024u;
+    return (uint32_t)pick_vec(a, o.vec, false) * (uint32_t)pick_block(o);
 }
 
 template <class E>

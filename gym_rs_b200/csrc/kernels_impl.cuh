@@ -43,7 +43,11 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
 }
 __device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v)
 {
+#ifdef GYMRS_DEBUG_RELAXED_PUBLISH // measurement only: NOT a correct publish
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
 }
 
 // ---- V-wide row access ------------------------------------------------------
@@ -295,6 +299,201 @@ step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Bat
     }
 }
 
+// ---- step, persistent TMA-staged stream ------------------------------------------
+// Same transition, different data movement.  The grid is persistent: G = (#SMs x CTAs per SM)
+// CTAs, CTA c walks the tiles c, c + G, c + 2G, ... of 1024 envs.  Each CTA keeps a ring of
+// STREAM_STAGES tiles in shared memory: one thread issues a bulk async copy (cp.async.bulk, the
+// 1-D TMA path -- UBLKCP in SASS) per input row of a tile, completing on that stage's mbarrier,
+// while the 256 threads consume the previous tile with conflict-free LDS.128 and store results
+// straight to global.  Compared with step_kernel this
+//   * always has a tile in flight per CTA, held in shared memory instead of registers, so the
+//     bytes in flight per SM no longer depend on how many register-heavy CTAs fit,
+//   * occupies only part of each SM, so with PDL the next launch's CTAs are co-resident from the
+//     start and stream in right behind (its trigger fires immediately: the grid is one wave),
+//   * replaces per-thread 64-bit address arithmetic + LDG by one LDS per row.
+// Chained-launch flags are per tile (1024 envs), the same granularity as step_kernel<V = 4> with
+// 256-thread CTAs, so the two kernels can follow each other in a chain.
+constexpr int TMA_TILE = 1024; // envs per tile = 256 threads x 4
+#ifndef GYMRS_STREAM_STAGES
+#define GYMRS_STREAM_STAGES 2
+#endif
+constexpr int STREAM_STAGES = GYMRS_STREAM_STAGES;
+
+template <class E, bool SBT, bool TL>
+struct TmaCfg {
+    static constexpr int ROWS = E::SD + 1 + (SBT ? 1 : 0) + (TL ? 1 : 0); // state rows, action row, optional rows
+    static constexpr size_t SMEM = (size_t)STREAM_STAGES * ROWS * TMA_TILE * 4 + STREAM_STAGES * 8;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy; bytes must be a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// spin until chain_flags[t] == want (thread 0 only); bounded, see step_kernel
+__device__ __forceinline__ void chain_wait(const BatchArgs &a, uint64_t t, uint32_t want)
+{
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(a.chain_flags + t) != want) {
+        __nanosleep(32);
+        if ((++spins & 1023u) == 0 && (spins > (1u << 17) || ld_acquire_gpu(a.chain_flags - 1) != 0u)) {
+            st_release_gpu(a.chain_flags - 1, 1u);
+            *reinterpret_cast<volatile uint32_t *>(a.err + 3) = 1u;
+            break;
+        }
+    }
+}
+
+#ifndef GYMRS_STREAM_MIN_CTAS
+#define GYMRS_STREAM_MIN_CTAS 5
+#endif
+
+template <class E, bool AR, bool SBT, bool TL>
+__global__ void __launch_bounds__(256, GYMRS_STREAM_MIN_CTAS)
+step_stream_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ BatchArgs a)
+{
+    using A = typename E::Action;
+    constexpr int V = 4, S = STREAM_STAGES;
+    constexpr int ROWS = TmaCfg<E, SBT, TL>::ROWS;
+    constexpr int R_ACT = E::SD, R_SBT = E::SD + 1, R_EL = E::SD + 1 + (SBT ? 1 : 0);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float(*tile)[ROWS][TMA_TILE] = reinterpret_cast<float(*)[ROWS][TMA_TILE]>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * ROWS * TMA_TILE * 4);
+
+    const uint64_t ntiles = (a.n + TMA_TILE - 1) / TMA_TILE;
+    const uint64_t G = gridDim.x;
+    // this CTA's k-th tile is tile_of(k); it owns K of them
+    const uint32_t K = blockIdx.x < ntiles ? (uint32_t)((ntiles - blockIdx.x + G - 1) / G) : 0u;
+    auto tile_of = [&](uint32_t k) -> uint64_t { return blockIdx.x + (uint64_t)k * G; };
+    auto tile_envs = [&](uint64_t t) -> uint32_t { // envs in tile t (n % 4 == 0 is a launch precondition)
+        const uint64_t left = a.n - t * TMA_TILE;
+        return left < (uint64_t)TMA_TILE ? (uint32_t)left : (uint32_t)TMA_TILE;
+    };
+    // thread 0 only: arm the stage's barrier and (optionally) fetch the action row
+    auto arm = [&](uint32_t k) {
+        const uint64_t t = tile_of(k);
+        const uint32_t bytes = tile_envs(t) * 4u;
+        mbar_expect_tx(&full[k % S], ROWS * bytes);
+        if (a.early_actions)
+            bulk_g2s(tile[k % S][R_ACT], reinterpret_cast<const A *>(a.actions) + t * TMA_TILE, bytes, &full[k % S]);
+    };
+    // thread 0 only: fetch everything the previous step of this handle may have written
+    auto fetch = [&](uint32_t k) {
+        const uint64_t t = tile_of(k), e0 = t * TMA_TILE;
+        const uint32_t bytes = tile_envs(t) * 4u;
+        const int st = k % S;
+#pragma unroll
+        for (int r = 0; r < E::SD; ++r) bulk_g2s(tile[st][r], a.state + r * a.ld + e0, bytes, &full[st]);
+        if (!a.early_actions) bulk_g2s(tile[st][R_ACT], reinterpret_cast<const A *>(a.actions) + e0, bytes, &full[st]);
+        if (SBT) bulk_g2s(tile[st][R_SBT], a.sbt + e0, bytes, &full[st]);
+        if (TL) bulk_g2s(tile[st][R_EL], a.elapsed + e0, bytes, &full[st]);
+    };
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int st = 0; st < S; ++st) mbar_init(&full[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // prologue: fill the ring
+    const uint32_t K0 = K < (uint32_t)S ? K : (uint32_t)S;
+    if (threadIdx.x == 0)
+        for (uint32_t k = 0; k < K0; ++k) arm(k);
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        if (a.chain) {
+            // per-tile dependency on the same tile of the handle's previous step; the rows were
+            // written through the generic proxy and are read below through the async proxy
+            for (uint32_t k = 0; k < K0; ++k) chain_wait(a, tile_of(k), a.chain_seq - 1u);
+            asm volatile("fence.proxy.async;" ::: "memory");
+        } else {
+            pdl_wait();
+        }
+        for (uint32_t k = 0; k < K0; ++k) fetch(k);
+    }
+    // everybody's stores must come after the previous grid when there is no per-tile chain
+    if (!a.chain) pdl_wait();
+
+    const uint32_t il = threadIdx.x * V; // first env of this thread inside a tile
+#pragma unroll 1
+    for (uint32_t k = 0; k < K; ++k) {
+        if (k > 0) {
+            // every thread has finished tile k - 1 (reads of its stage and all its stores):
+            // publish it and refill its stage with the tile S positions ahead
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (a.publish) st_release_gpu(a.chain_flags + tile_of(k - 1), a.chain_seq);
+                if (k - 1 + S < K) {
+                    arm(k - 1 + S);
+                    if (a.chain) {
+                        chain_wait(a, tile_of(k - 1 + S), a.chain_seq - 1u);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
+                    fetch(k - 1 + S);
+                }
+            }
+        }
+        const int st = k % S;
+        const uint64_t t = tile_of(k);
+        mbar_wait(&full[st], (k / S) & 1u);
+        if (il < tile_envs(t)) {
+            const uint64_t i0 = t * TMA_TILE + il;
+            float s[E::SD][V], o[E::OD][V];
+            A act[V];
+            int32_t sbt[V];
+            uint32_t el[V];
+#pragma unroll
+            for (int r = 0; r < E::SD; ++r) unpack<V>(*reinterpret_cast<const float4 *>(&tile[st][r][il]), s[r]);
+            unpack<V>(*reinterpret_cast<const uint4 *>(&tile[st][R_ACT][il]), act);
+            if (SBT) unpack<V>(*reinterpret_cast<const int4 *>(&tile[st][R_SBT][il]), sbt);
+            if (TL) unpack<V>(*reinterpret_cast<const uint4 *>(&tile[st][R_EL][il]), el);
+
+            float rew[V];
+            uint8_t dn[V], tr[V];
+            transition<E, V, AR, SBT, TL>(p, a, s, o, act, sbt, el, rew, dn, tr, a.global_off + i0, a.epoch, V);
+#pragma unroll
+            for (int r = 0; r < E::SD; ++r) st_row<V, true>(a.state + r * a.ld + i0, s[r], V);
+            if (!E::OBS_IS_STATE) {
+#pragma unroll
+                for (int r = 0; r < E::OD; ++r) st_row<V, true>(a.obs + r * a.ld + i0, o[r], V);
+            }
+            st_row<V, true>(a.reward + i0, rew, V);
+            st_row<V, true>(a.done + i0, dn, V);
+            if (TL) st_row<V, true>(a.truncated + i0, tr, V);
+            if (SBT) st_row<V, true>(a.sbt + i0, sbt, V);
+            if (TL) st_row<V, true>(a.elapsed + i0, el, V);
+        }
+    }
+    if (a.publish && K > 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu(a.chain_flags + tile_of(K - 1), a.chain_seq);
+    }
+}
+
 // ---- fused rollout ------------------------------------------------------------
 // n_steps transitions in one launch.  State lives in registers; per step the kernel
 // reads one action row and streams out observation / reward / done.  The actions of
@@ -427,10 +626,72 @@ cudaError_t dispatch_flags(const typename E::P &p, const BatchArgs &a_in, const 
     return cudaErrorInvalidValue;
 }
 
+template <class K>
+cudaError_t allow_big_smem(K kernel, size_t bytes)
+{
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// persistent grid size: SMs of the current device x CTAs per SM (GYMRS_STREAM_CTAS_PER_SM, default 2)
+inline int stream_grid_slots()
+{
+    static const int per_sm = [] {
+        const char *e = std::getenv("GYMRS_STREAM_CTAS_PER_SM");
+        const int v = e ? std::atoi(e) : 2;
+        return v >= 1 && v <= 8 ? v : 2;
+    }();
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * per_sm;
+}
+
+template <class E>
+cudaError_t dispatch_tma(const typename E::P &p, const BatchArgs &a_in, const LaunchOpts &o, cudaStream_t s)
+{
+    const bool sbt = E::HAS_SBT && o.use_sbt;
+    BatchArgs a = a_in;
+    a.early_actions = (o.pdl == 2);
+    if (o.pdl == 0) { a.early_actions = 0; a.chain = 0; }
+    const uint64_t tiles = (a.n + TMA_TILE - 1) / TMA_TILE;
+    cudaLaunchConfig_t cfg = {};
+    const uint64_t slots = (uint64_t)stream_grid_slots();
+    cfg.gridDim = dim3((unsigned)(tiles < slots ? tiles : slots));
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = o.pdl != 0 ? 1 : 0;
+    const int key = (o.autoreset ? 4 : 0) | (sbt ? 2 : 0) | (o.time_limit ? 1 : 0);
+#define GYMRS_CASE(K, AR, SB, TL)                                                      \
+    case K: {                                                                          \
+        auto kern = step_stream_kernel<E, AR, SB, TL>;                                    \
+        cfg.dynamicSmemBytes = TmaCfg<E, SB, TL>::SMEM;                                \
+        cudaError_t e = allow_big_smem(kern, cfg.dynamicSmemBytes);                    \
+        if (e != cudaSuccess) return e;                                                \
+        return cudaLaunchKernelEx(&cfg, kern, p, a);                                   \
+    }
+    switch (key) {
+        GYMRS_CASE(0, false, false, false)
+        GYMRS_CASE(1, false, false, true)
+        GYMRS_CASE(2, false, true, false)
+        GYMRS_CASE(3, false, true, true)
+        GYMRS_CASE(4, true, false, false)
+        GYMRS_CASE(5, true, false, true)
+        GYMRS_CASE(6, true, true, false)
+        GYMRS_CASE(7, true, true, true)
+    }
+#undef GYMRS_CASE
+    return cudaErrorInvalidValue;
+}
+
 template <class E, bool ROLLOUT>
 cudaError_t dispatch_vec(const typename E::P &p, const BatchArgs &a, const LaunchOpts &o, cudaStream_t s)
 {
     if (a.n == 0) return cudaSuccess;
+    if (!ROLLOUT && use_tma_step(a, o)) return dispatch_tma<E>(p, a, o, s);
     switch (pick_vec(a, o.vec, ROLLOUT)) {
     case 4: return dispatch_flags<E, 4, ROLLOUT>(p, a, o, s);
     case 2: return dispatch_flags<E, 2, ROLLOUT>(p, a, o, s);

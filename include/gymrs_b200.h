@@ -183,7 +183,9 @@ int gymrs_kind_of(const gymrs_env *env, int *kind);
 int gymrs_sync(gymrs_env *env, uint64_t *bad_env);
 
 /* Launch tuning (not part of the reference surface).
- * vec: env instances per thread, 0 = widest the buffer alignment allows (4), or 1 / 2 / 4.
+ * vec: env instances per thread, 0 = widest the buffer alignment allows (4), or 1 / 2 / 4;
+ *      8 selects the persistent TMA-staged variant (cp.async.bulk into a shared-memory ring,
+ *      4 envs per thread), which falls back to the plain kernel when alignment does not allow it.
  * block: threads per CTA, 0 = 256.
  * pdl: 0 = plain stream order.
  *      1 (default) = programmatic dependent launch: the next step's CTAs are scheduled while the

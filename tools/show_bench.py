@@ -3,6 +3,8 @@ tag=sys.argv[1]
 try:
     d=json.loads(sys.stdin.read())
     r=d.get("rollout") or {}
-    print("%s us/step=%.3f frac=%.3f resident_us=%.3f rollout=%.4g rfrac=%.3f clk=%s %s" % (tag, d["ms_per_step"]*1e3, d["roofline"]["frac"], d["l2_resident"]["ms_per_step"]*1e3, r.get("value",0), r.get("frac",0), d["clocks"]["sm_mhz"], d["clocks"]["reasons"]))
+    c=d.get("single_stream_chained") or {}
+    e=d.get("e2e") or {}
+    print("%s us/step=%.3f frac=%.3f chained_us=%.3f resident_us=%.3f rollout=%.4g rfrac=%.3f e2e=%.3g clk=%s %s" % (tag, d["ms_per_step"]*1e3, d["roofline"]["frac"], c.get("ms_per_step",0)*1e3, d["l2_resident"]["ms_per_step"]*1e3, r.get("value",0), r.get("frac",0), e.get("value",0), d["clocks"]["sm_mhz"], d["clocks"]["reasons"]))
 except Exception as e:
     print(tag, "FAILED", e)
