@@ -63,6 +63,8 @@ SIGNATURES = {
     "gymrs_reset": (_i, [_vp, _pu64, _vp, _vp, _vp, _pu64]),
     "gymrs_step": (_i, [_vp, _vp, _u32]),
     "gymrs_step_host": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "gymrs_step_host_async": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _pu64]),
+    "gymrs_host_wait": (_i, [_vp, _u64]),
     "gymrs_rollout": (_i, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "gymrs_get_state": (_i, [_vp, _vp, _vp]),
     "gymrs_set_state": (_i, [_vp, _vp, _vp]),

@@ -273,6 +273,23 @@ class Env(EnvProperties):
         _capi.check(self._L.gymrs_step_host(self._h, hp(actions), flags, hp(obs), hp(reward), hp(done),
                                             hp(truncated)))
 
+    def step_host_async(self, actions, obs, reward, done, truncated=None, autoreset: bool = False) -> int:
+        """gymrs_step_host_async: like step_host but returns a ticket at once; the host buffers must
+        not be touched until host_wait(ticket).  Two steps may be in flight (double buffering)."""
+        flags = _capi.STEP_AUTORESET if autoreset else 0
+
+        def hp(a):
+            if a is None:
+                return None
+            return C.c_void_p(a.data_ptr()) if hasattr(a, "data_ptr") else a.ctypes.data_as(C.c_void_p)
+        ticket = C.c_uint64()
+        _capi.check(self._L.gymrs_step_host_async(self._h, hp(actions), flags, hp(obs), hp(reward), hp(done),
+                                                  hp(truncated), C.byref(ticket)))
+        return int(ticket.value)
+
+    def host_wait(self, ticket: int):
+        _capi.check(self._L.gymrs_host_wait(self._h, int(ticket)))
+
     def rollout(self, actions, obs_out=None, reward_out=None, done_out=None, autoreset: bool = True):
         """gymrs_rollout: actions [n_steps, num_envs] on the device; fused multi-step launch."""
         n_steps = int(actions.shape[0])

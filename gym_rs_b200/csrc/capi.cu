@@ -13,6 +13,7 @@
 #include <new>
 #include <random>
 #include <string>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -71,6 +72,17 @@ void make_reset_box(ResetBox &rb, int dim, const float *low, const float *high)
 
 } // namespace
 
+// event slots of the host-buffer pipeline
+struct HostEv {
+    static constexpr int CHUNKS = 8;
+    static constexpr int in_ready(int par, int c) { return par * CHUNKS + c; }
+    static constexpr int out_ready(int par, int c) { return 2 * CHUNKS + par * CHUNKS + c; }
+    static constexpr int copied(int c) { return 4 * CHUNKS + c; }
+    static constexpr int host_done(int par) { return 5 * CHUNKS + par; }
+    static constexpr int FENCE = 5 * CHUNKS + 2;
+    static constexpr int COUNT = 5 * CHUNKS + 3;
+};
+
 struct gymrs_env {
     int kind = 0;
     uint64_t n = 0, ld = 0, global_off = 0;
@@ -101,7 +113,9 @@ struct gymrs_env {
 
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_streams[2] = {nullptr, nullptr};
-    cudaEvent_t ev[8] = {};
+    std::vector<cudaEvent_t> hev; // events of the host-buffer pipeline (HostEv), created on first use
+    uint64_t host_seq = 0;        // tickets handed out by gymrs_step_host_async
+    bool host_inflight = false;   // a host step may still be copying results out
 
     uint64_t seed = 0;       // Philox key of the auto-reset stream
     uint64_t step_count = 0; // steps since the last full reset; epoch of an auto-reset = step_count + 1
@@ -251,6 +265,17 @@ uint64_t entropy64()
     return ((uint64_t)rd() << 32) ^ (uint64_t)rd();
 }
 
+// A host step submitted with gymrs_step_host_async may still be copying results out of the
+// handle's arrays; every other entry point that touches them waits for that first.
+int drain_host(gymrs_env *e)
+{
+    if (!e->host_inflight) return GYMRS_OK;
+    CU(cudaStreamSynchronize(e->copy_streams[0]));
+    CU(cudaStreamSynchronize(e->copy_streams[1]));
+    e->host_inflight = false;
+    return GYMRS_OK;
+}
+
 void after_step(gymrs_env *e, uint32_t step_flags, uint32_t n_steps)
 {
     e->step_count += n_steps;
@@ -261,6 +286,7 @@ int free_env(gymrs_env *e)
 {
     if (!e) return GYMRS_OK;
     cudaSetDevice(e->device);
+    for (auto &s : e->copy_streams) if (s) cudaStreamSynchronize(s);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     cudaFree(e->state);
     if (e->obs && e->obs != e->state) cudaFree(e->obs);
@@ -273,7 +299,7 @@ int free_env(gymrs_env *e)
     cudaFree(e->chain_mem);
     if (e->err_host) cudaFreeHost(e->err_host);
     for (auto &s : e->copy_streams) if (s) cudaStreamDestroy(s);
-    for (auto &v : e->ev) if (v) cudaEventDestroy(v);
+    for (auto &v : e->hev) if (v) cudaEventDestroy(v);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return GYMRS_OK;
@@ -288,7 +314,6 @@ int alloc_env(gymrs_env *e)
     CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
     for (auto &s : e->copy_streams) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    for (auto &v : e->ev) CU(cudaEventCreateWithFlags(&v, cudaEventDisableTiming));
     CU(cudaMalloc(&e->state, sizeof(float) * e->state_dim * e->ld));
     CU(cudaMemsetAsync(e->state, 0, sizeof(float) * e->state_dim * e->ld, e->stream));
     if (e->kind == GYMRS_PENDULUM) {
@@ -446,8 +471,9 @@ int gymrs_clone(const gymrs_env *src, gymrs_env **out)
         free_env(e);
         return fail(rc, msg);
     }
-    // order the copies after everything already queued on the source's stream
+    // order the copies after everything already queued on the source's streams
     cudaError_t ce = cudaStreamSynchronize(src->stream);
+    for (auto &s : src->copy_streams) if (ce == cudaSuccess && s) ce = cudaStreamSynchronize(s);
     auto cp = [&](void *d, const void *s, size_t b) {
         if (ce == cudaSuccess && d && s) ce = cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, e->stream);
     };
@@ -490,6 +516,7 @@ int gymrs_set_stream(gymrs_env *e, void *cuda_stream)
 {
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
     CU(cudaSetDevice(e->device));
+    if (int rc_ = drain_host(e)) return rc_;
     CU(cudaStreamSynchronize(e->stream));
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
     return GYMRS_OK;
@@ -519,6 +546,7 @@ int gymrs_reset(gymrs_env *e, const uint64_t *seed, const float *low, const floa
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
     if ((low == nullptr) != (high == nullptr)) return fail(GYMRS_ERR_BAD_ARG, "low and high must be given together");
     CU(cudaSetDevice(e->device));
+    if (int rc_ = drain_host(e)) return rc_;
     const uint64_t s = seed ? *seed : entropy64(); // seeding.rs:22
     if (seed_used) *seed_used = s;
     // `options: Option<BoxR<Obs>>` applies to this call only (cartpole.rs:351-365)
@@ -556,6 +584,7 @@ int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
 {
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     CU(cudaSetDevice(e->device));
+    if (int rc_ = drain_host(e)) return rc_;
     BatchArgs a = base_args(e);
     a.actions = actions;
     const LaunchOpts o = make_opts(e, step_flags);
@@ -574,36 +603,65 @@ int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
     return GYMRS_OK;
 }
 
-int gymrs_step_host(gymrs_env *e, const void *actions, uint32_t step_flags,
-                    float *obs, float *reward, uint8_t *done, uint8_t *truncated)
+// Host-buffer step, asynchronous.  Chunked pipeline over three streams:
+//   h2d:  actions chunk c            -> staging[ticket % 2]
+//   cs :  step kernel on chunk c     (after its actions arrived AND the previous host step's
+//                                     copy-out of chunk c finished: the result arrays are reused)
+//   d2h:  observation / reward / done of chunk c -> caller's buffers
+// Chunk c + 1's copy-in and chunk c - 1's copy-out overlap chunk c's kernel, and because nothing
+// here blocks the host, step t + 1 can be submitted while step t's results are still streaming
+// out: the D2H engine (the bottleneck at 21 B per env-step vs 4 B in) never idles.  Chunk
+// boundaries are multiples of 1024 envs so every chunk keeps the 128-bit access path.
+int gymrs_step_host_async(gymrs_env *e, const void *actions, uint32_t step_flags,
+                          float *obs, float *reward, uint8_t *done, uint8_t *truncated, uint64_t *ticket)
 {
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     CU(cudaSetDevice(e->device));
-    if (!e->d_actions) CU(cudaMalloc(&e->d_actions, 4 * e->ld));
-    e->chain_ok = false; // the slice launches below use their own CTA numbering
-    // Chunked three-stage pipeline: H2D(actions) -> step -> D2H(results), chunk c+1's copy-in
-    // and chunk c-1's copy-out overlap chunk c's kernel.  Chunk boundaries are multiples of
-    // 1024 envs so every chunk keeps the 128-bit access path.
     const uint64_t n = e->n;
-    uint64_t nchunk = n >= (1u << 18) ? 4 : 1;
-    uint64_t per = ((n + nchunk - 1) / nchunk + 1023) / 1024 * 1024;
+    const uint64_t tk = e->host_seq;
+    const int par = (int)(tk & 1);
+    if (!e->d_actions) CU(cudaMalloc(&e->d_actions, 2 * 4 * e->ld)); // two staging buffers
+    if (e->hev.empty()) {
+        e->hev.resize(HostEv::COUNT);
+        for (auto &v : e->hev) CU(cudaEventCreateWithFlags(&v, cudaEventDisableTiming));
+    }
+    e->chain_ok = false; // the slice launches below use their own CTA numbering
+    // Chunk count: PCIe copies below ~2 MB lose bandwidth (measured on the B200 box: 512 KB
+    // copies reach 42 GB/s, 4 MB copies 54 GB/s), so rows are split into at most a few pieces,
+    // each at least 256 K envs (1 MB per f32 row).  GYMRS_HOST_CHUNKS overrides for experiments.
+    static const int chunk_override = [] {
+        const char *s = std::getenv("GYMRS_HOST_CHUNKS");
+        const int v = s ? std::atoi(s) : 0;
+        return v >= 1 && v <= HostEv::CHUNKS ? v : 0;
+    }();
+    uint64_t nchunk = chunk_override ? (uint64_t)chunk_override : 2;
+    while (nchunk > 1 && n / nchunk < (1u << 18)) --nchunk;
+    const uint64_t per = ((n + nchunk - 1) / nchunk + 1023) / 1024 * 1024;
     cudaStream_t h2d = e->copy_streams[0], d2h = e->copy_streams[1], cs = e->stream;
+    char *staging = (char *)e->d_actions + (size_t)par * 4 * e->ld;
     LaunchOpts o = make_opts(e, step_flags);
     o.pdl = 0;
-    // everything queued earlier on the compute stream (reset, set_state) precedes the copies
-    CU(cudaEventRecord(e->ev[7], cs));
-    CU(cudaStreamWaitEvent(h2d, e->ev[7], 0));
-    CU(cudaStreamWaitEvent(d2h, e->ev[7], 0));
+    if (!e->host_inflight) {
+        // everything queued earlier on the compute stream (reset, set_state, device steps)
+        // precedes this host step's copies
+        CU(cudaEventRecord(e->hev[HostEv::FENCE], cs));
+        CU(cudaStreamWaitEvent(h2d, e->hev[HostEv::FENCE], 0));
+        CU(cudaStreamWaitEvent(d2h, e->hev[HostEv::FENCE], 0));
+    }
     int c = 0;
     for (uint64_t b = 0; b < n; b += per, ++c) {
         const uint64_t cnt = (b + per <= n) ? per : n - b;
-        cudaEvent_t in_ready = e->ev[c % 3], out_ready = e->ev[3 + c % 3];
-        CU(cudaMemcpyAsync((char *)e->d_actions + 4 * b, (const char *)actions + 4 * b, 4 * cnt,
-                           cudaMemcpyHostToDevice, h2d));
+        cudaEvent_t in_ready = e->hev[HostEv::in_ready(par, c)], out_ready = e->hev[HostEv::out_ready(par, c)],
+                    copied = e->hev[HostEv::copied(c)];
+        // staging[par] chunk c was last read by the kernel of host step tk - 2
+        if (tk >= 2) CU(cudaStreamWaitEvent(h2d, out_ready, 0));
+        CU(cudaMemcpyAsync(staging + 4 * b, (const char *)actions + 4 * b, 4 * cnt, cudaMemcpyHostToDevice, h2d));
         CU(cudaEventRecord(in_ready, h2d));
         CU(cudaStreamWaitEvent(cs, in_ready, 0));
+        // the result rows of chunk c are still being copied out for host step tk - 1
+        if (e->host_inflight) CU(cudaStreamWaitEvent(cs, copied, 0));
         BatchArgs a = slice_args(e, b, cnt);
-        a.actions = (const char *)e->d_actions + 4 * b;
+        a.actions = staging + 4 * b;
         CU(do_step(e, a, o, cs, false));
         CU(cudaEventRecord(out_ready, cs));
         CU(cudaStreamWaitEvent(d2h, out_ready, 0));
@@ -613,10 +671,41 @@ int gymrs_step_host(gymrs_env *e, const void *actions, uint32_t step_flags,
         if (reward) CU(cudaMemcpyAsync(reward + b, e->reward + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, d2h));
         if (done) CU(cudaMemcpyAsync(done + b, e->done + b, cnt, cudaMemcpyDeviceToHost, d2h));
         if (truncated) CU(cudaMemcpyAsync(truncated + b, e->truncated + b, cnt, cudaMemcpyDeviceToHost, d2h));
+        CU(cudaEventRecord(copied, d2h));
     }
+    CU(cudaEventRecord(e->hev[HostEv::host_done(par)], d2h));
     after_step(e, step_flags, 1);
-    CU(cudaStreamSynchronize(d2h));
-    CU(cudaStreamSynchronize(cs));
+    e->host_inflight = true;
+    e->host_seq = tk + 1;
+    if (ticket) *ticket = tk;
+    return GYMRS_OK;
+}
+
+int gymrs_host_wait(gymrs_env *e, uint64_t ticket)
+{
+    if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
+    if (ticket >= e->host_seq) return fail(GYMRS_ERR_BAD_ARG, "unknown ticket");
+    if (e->hev.empty() || ticket + 2 < e->host_seq) return GYMRS_OK; // its event slot was re-recorded by a later, waited step
+    CU(cudaSetDevice(e->device));
+    // a slot re-recorded by ticket + 2 can only make this wait longer, never shorter
+    CU(cudaEventSynchronize(e->hev[HostEv::host_done((int)(ticket & 1))]));
+    if (ticket + 1 == e->host_seq) {
+        // newest host step: nothing of it is in flight any more
+        CU(cudaStreamSynchronize(e->copy_streams[1]));
+        e->host_inflight = false;
+    }
+    return GYMRS_OK;
+}
+
+int gymrs_step_host(gymrs_env *e, const void *actions, uint32_t step_flags,
+                    float *obs, float *reward, uint8_t *done, uint8_t *truncated)
+{
+    uint64_t ticket = 0;
+    int rc = gymrs_step_host_async(e, actions, step_flags, obs, reward, done, truncated, &ticket);
+    if (rc != GYMRS_OK) return rc;
+    rc = gymrs_host_wait(e, ticket);
+    if (rc != GYMRS_OK) return rc;
+    CU(cudaStreamSynchronize(e->stream));
     return GYMRS_OK;
 }
 
@@ -626,6 +715,7 @@ int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t 
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     if (n_steps == 0) return GYMRS_OK;
     CU(cudaSetDevice(e->device));
+    if (int rc_ = drain_host(e)) return rc_;
     BatchArgs a = base_args(e);
     a.actions = actions;
     a.n_steps = n_steps;
@@ -644,6 +734,7 @@ int gymrs_get_state(gymrs_env *e, float *state, int32_t *sbt)
 {
     if (!e || !state) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     CU(cudaSetDevice(e->device));
+    if (int rc_ = drain_host(e)) return rc_;
     CU(cudaMemcpy2DAsync(state, sizeof(float) * e->n, e->state, sizeof(float) * e->ld,
                          sizeof(float) * e->n, e->state_dim, cudaMemcpyDeviceToHost, e->stream));
     if (sbt) {
@@ -658,6 +749,7 @@ int gymrs_set_state(gymrs_env *e, const float *state, const int32_t *sbt)
 {
     if (!e || !state) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     CU(cudaSetDevice(e->device));
+    if (int rc_ = drain_host(e)) return rc_;
     e->chain_ok = false;
     CU(cudaMemcpy2DAsync(e->state, sizeof(float) * e->ld, state, sizeof(float) * e->n,
                          sizeof(float) * e->n, e->state_dim, cudaMemcpyHostToDevice, e->stream));
@@ -754,6 +846,7 @@ int gymrs_sync(gymrs_env *e, uint64_t *bad_env)
 {
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
     CU(cudaSetDevice(e->device));
+    if (int rc_ = drain_host(e)) return rc_;
     CU(cudaStreamSynchronize(e->stream));
     if (e->err_host[3]) {
         e->err_host[3] = 0;

@@ -154,6 +154,15 @@ int gymrs_step(gymrs_env *env, const void *actions, uint32_t step_flags);
 int gymrs_step_host(gymrs_env *env, const void *actions, uint32_t step_flags,
                     float *obs, float *reward, uint8_t *done, uint8_t *truncated);
 
+/* Asynchronous form of gymrs_step_host for pipelined host loops (pinned host delivery overlapped
+ * with the next step): enqueues copy-in, step and copy-out and returns at once; *ticket
+ * identifies the step.  The host buffers belong to the library until gymrs_host_wait(env, ticket)
+ * returns.  Up to two host steps may be in flight (use two sets of host buffers); every other
+ * entry point on the handle first waits for them. */
+int gymrs_step_host_async(gymrs_env *env, const void *actions, uint32_t step_flags,
+                          float *obs, float *reward, uint8_t *done, uint8_t *truncated, uint64_t *ticket);
+int gymrs_host_wait(gymrs_env *env, uint64_t ticket);
+
 /* Fused rollout: n_steps consecutive steps in ONE launch, state held in registers.
  * actions: device [n_steps][num_envs].  Per-step results are streamed to the caller's
  * device arrays (any may be NULL): obs_out [n_steps][obs_dim][num_envs],

@@ -594,6 +594,54 @@ def test_step_host_equals_device_step(torch, g):
     b.close()
 
 
+def test_async_host_pipeline_equals_synchronous_host_steps(torch, g):
+    """gymrs_step_host_async / gymrs_host_wait (double-buffered pinned delivery overlapped with the
+    next step) must deliver exactly what the synchronous host step delivers, step by step, and
+    other entry points must wait for in-flight host steps."""
+    n = (1 << 20) + 4096
+    a = g.MountainCarEnv(num_envs=n)
+    b = g.MountainCarEnv(num_envs=n)
+    for e in (a, b):
+        e.reset(seed=8)
+    r = np.random.default_rng(2)
+    acts = [torch.as_tensor(r.integers(0, 3, n).astype(np.int32)).pin_memory() for _ in range(6)]
+    bufs = [dict(obs=torch.empty((2, n), dtype=torch.float32).pin_memory(),
+                 rew=torch.empty(n, dtype=torch.float32).pin_memory(),
+                 done=torch.empty(n, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+    ref = dict(obs=torch.empty((2, n), dtype=torch.float32).pin_memory(),
+               rew=torch.empty(n, dtype=torch.float32).pin_memory(),
+               done=torch.empty(n, dtype=torch.uint8).pin_memory())
+    tickets = []
+    expected = []
+    for t, act in enumerate(acts):
+        s = bufs[t % 2]
+        if t >= 2:  # this buffer set is about to be reused: its step must be finished and checked
+            a.host_wait(tickets[t - 2])
+            assert torch.equal(s["obs"], expected[t - 2][0]) and torch.equal(s["done"], expected[t - 2][2])
+        tickets.append(a.step_host_async(act, s["obs"], s["rew"], s["done"], None, autoreset=True))
+        b.step_host(act, ref["obs"], ref["rew"], ref["done"], None, autoreset=True)
+        expected.append((ref["obs"].clone(), ref["rew"].clone(), ref["done"].clone()))
+    for t in (len(acts) - 2, len(acts) - 1):
+        a.host_wait(tickets[t])
+        s = bufs[t % 2]
+        assert torch.equal(s["obs"], expected[t][0])
+        assert torch.equal(s["rew"], expected[t][1])
+        assert torch.equal(s["done"], expected[t][2])
+    # a device step right after an un-waited async host step is ordered after it
+    tk = a.step_host_async(acts[0], bufs[0]["obs"], bufs[0]["rew"], bufs[0]["done"], None, autoreset=True)
+    da = acts[1].cuda()
+    out = a.step(da, autoreset=True)
+    a.sync()
+    a.host_wait(tk)
+    b.step_host(acts[0], ref["obs"], ref["rew"], ref["done"], None, autoreset=True)
+    assert torch.equal(bufs[0]["obs"], ref["obs"])
+    ob = b.step(da, autoreset=True)
+    b.sync()
+    assert torch.equal(out.observation, ob.observation)
+    a.close()
+    b.close()
+
+
 def test_sharding_invariance_at_full_size(torch, g):
     """results are keyed by GLOBAL env id, so one 1M-env handle and two
     512K-env handles (as two GPUs would hold them) produce identical bits."""
