@@ -1,0 +1,56 @@
+"""Multi-GPU device tests (need >= 2 GPUs; skipped otherwise): two ranks hold shards of one logical
+batch, step them with no collective, and the optional NCCL all-gather view equals a single-GPU run."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import torch
+    import torch.distributed as dist
+    import gym_rs_b200 as g
+    from gym_rs_b200.sharding import make_sharded_env, gather_observations
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    total = (1 << 18) + 2 * 1024
+    env = make_sharded_env(g.CartPoleEnv, total, rank, world, rank)
+    env.reset(seed=21)
+    gen = torch.Generator(device="cuda").manual_seed(5)       # same stream of actions on every rank
+    b, e = (rank * total // world, (rank + 1) * total // world)
+    for t in range(30):
+        acts = torch.randint(0, 2, (total,), generator=gen, device="cuda", dtype=torch.int32)
+        env.step(acts[b:e].contiguous(), autoreset=True)       # NO collective on the step path
+    view = gather_observations(env, total)
+    if rank == 0:
+        whole = g.CartPoleEnv(num_envs=total, device=0)
+        whole.reset(seed=21)
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        for t in range(30):
+            acts = torch.randint(0, 2, (total,), generator=gen, device="cuda", dtype=torch.int32)
+            out = whole.step(acts, autoreset=True)
+        whole.sync()
+        assert torch.equal(view, out.observation), "sharded run differs from the single-GPU run"
+        print("MULTI_GPU_OK")
+    dist.barrier()
+    dist.destroy_process_group()
+""")
+
+
+def test_two_rank_shards_equal_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29581", str(script)],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -82,3 +82,15 @@ def test_bench_line_contract_fields():
         assert k in d, k
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
     assert "workload" in d["config"] and "MountainCar" in d["config"]["workload"]
+
+
+def test_shard_range_partitions_exactly():
+    from gym_rs_b200.sharding import shard_range
+    for total, world in ((1 << 23, 8), (1 << 20, 1), (1000003, 8), (5, 8), (0, 3)):
+        ranges = [shard_range(r, world, total) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == total
+        for (b0, e0), (b1, e1) in zip(ranges, ranges[1:]):
+            assert e0 == b1 and e0 >= b0
+        sizes = [e - b for b, e in ranges]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard_range(3, 8, 1 << 23) == (3 << 20, 4 << 20)   # BASELINE config 5: 1M envs per GPU
