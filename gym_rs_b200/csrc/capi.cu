@@ -883,11 +883,15 @@ int gymrs_host_free(void *p)
     return GYMRS_OK;
 }
 
-// utils/custom/util_fns.rs:2-10
+// utils/custom/util_fns.rs:2-10 on O64 = OrderedFloat<f64> (types.rs:4): same branch order, with
+// OrderedFloat's total order (NaN == NaN, NaN greater than everything else), so a NaN value is
+// clipped to the right bound.
 double gymrs_clip(double value, double left_bound, double right_bound)
 {
-    if (left_bound <= value && value <= right_bound) return value;
-    else if (value > right_bound) return right_bound;
+    auto le = [](double a, double b) { return a <= b || (b != b); };           // a <= b in the total order
+    auto gt = [](double a, double b) { return a > b || (a != a && b == b); };  // a >  b in the total order
+    if (le(left_bound, value) && le(value, right_bound)) return value;
+    else if (gt(value, right_bound)) return right_bound;
     else return left_bound;
 }
 

@@ -112,8 +112,9 @@ struct CartPole {
         }
         s[0] = nx; s[1] = nxd; s[2] = nth; s[3] = nthd;
         // strict comparisons on the updated x, theta                                 :450-453
-        // (x < -T || x > T) == (|x| > T), NaN included (all false)
-        done = (fabsf(nx) > p.x_thr) | (fabsf(nth) > p.th_thr);
+        // (x < -T || x > T) == (|x| > T).  The reference compares OrderedFloat values, a total
+        // order in which NaN is greater than everything, so a NaN state IS done: !(|x| <= T).
+        done = !(fabsf(nx) <= p.x_thr) | !(fabsf(nth) <= p.th_thr);
         reward = 1.0f;
     }
 
@@ -140,6 +141,15 @@ struct MountainCarP {
     ResetBox rb;       // :176-187 position in [-0.6, -0.4); velocity is always 0 (:162-167)
 };
 
+// clip (util_fns.rs:2-10) on OrderedFloat values: in range -> value, greater than the right bound
+// -> right bound, else left bound.  OrderedFloat's total order puts NaN above everything, so a
+// NaN value is clipped to the RIGHT bound (fminf / fmaxf would return the left one).
+__device__ __forceinline__ float clip_of(float v, float lo, float hi)
+{
+    v = !(v <= hi) ? hi : v;
+    return v < lo ? lo : v;
+}
+
 struct MountainCar {
     static constexpr int SD = 2, OD = 2;
     static constexpr bool OBS_IS_STATE = true;
@@ -156,10 +166,9 @@ struct MountainCar {
         // velocity += (a - 1) * force + cos(3 * position) * (-gravity)               :411-412
         const float rhs = fmaf(cosf(3.0f * position), p.neg_gravity, (float)(a - 1) * p.force);
         velocity += rhs;
-        // clip (util_fns.rs:2-10); fmin/fmax is the same function for non-NaN input  :413
-        velocity = fminf(fmaxf(velocity, -p.max_speed), p.max_speed);
+        velocity = clip_of(velocity, -p.max_speed, p.max_speed); //                  :413
         position += velocity; //                                                      :415
-        position = fminf(fmaxf(position, p.min_position), p.max_position); //         :416
+        position = clip_of(position, p.min_position, p.max_position); //              :416
         // exact equality with the clipped wall value                                 :418-420
         if (position == p.min_position && velocity < 0.0f) velocity = 0.0f;
         done = (position >= p.goal_position) & (velocity >= p.goal_velocity); //      :422

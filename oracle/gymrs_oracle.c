@@ -28,12 +28,32 @@
 /* shared                                                                    */
 /* ------------------------------------------------------------------------ */
 
-/* src/utils/custom/util_fns.rs:2-10 */
+/* Comparisons of O64 = ordered_float::OrderedFloat<f64> (src/utils/custom/types.rs:4).  The
+ * reference never compares raw f64: OrderedFloat's Ord/PartialOrd is a TOTAL order in which NaN
+ * equals NaN and is greater than every other value (ordered-float >= 3.9.1, Cargo.toml:33).  For
+ * finite and infinite values these are the IEEE comparisons; they differ only on NaN. */
+static int of_cmp(double a, double b)
+{
+    if (a < b) return -1;
+    if (a > b) return 1;
+    if (a == b) return 0;
+    /* at least one NaN */
+    if (a != a) return (b != b) ? 0 : 1;
+    return -1;
+}
+static int of_lt(double a, double b) { return of_cmp(a, b) < 0; }
+static int of_le(double a, double b) { return of_cmp(a, b) <= 0; }
+static int of_gt(double a, double b) { return of_cmp(a, b) > 0; }
+static int of_ge(double a, double b) { return of_cmp(a, b) >= 0; }
+static int of_eq(double a, double b) { return of_cmp(a, b) == 0; }
+
+/* src/utils/custom/util_fns.rs:2-10 instantiated on O64: a NaN value is "greater than" the right
+ * bound and is therefore clipped to it. */
 double orc_clip(double value, double left_bound, double right_bound)
 {
-    if (left_bound <= value && value <= right_bound) {
+    if (of_le(left_bound, value) && of_le(value, right_bound)) {
         return value;
-    } else if (value > right_bound) {
+    } else if (of_gt(value, right_bound)) {
         return right_bound;
     } else {
         return left_bound;
@@ -205,10 +225,10 @@ int orc_cartpole_step(orc_cartpole_env *env, size_t action,
     env->state[3] = theta_dot;
 
     /* :450-453 strict comparisons on the UPDATED x, theta */
-    int d = x < -p->x_threshold
-         || x > p->x_threshold
-         || theta < -p->theta_threshold_radians
-         || theta > p->theta_threshold_radians;
+    int d = of_lt(x, -p->x_threshold)
+         || of_gt(x, p->x_threshold)
+         || of_lt(theta, -p->theta_threshold_radians)
+         || of_gt(theta, p->theta_threshold_radians);
 
     /* :455-464 */
     double r;
@@ -303,12 +323,12 @@ int orc_mountain_car_step(orc_mountain_car_env *env, size_t action,
     position = orc_clip(position, p->min_position, p->max_position);
 
     /* :418-420 exact float equality after the clip */
-    if (position == p->min_position && velocity < 0.) {
+    if (of_eq(position, p->min_position) && of_lt(velocity, 0.)) {
         velocity = 0.;
     }
 
     /* :422-423 */
-    int d = position >= p->goal_position && velocity >= p->goal_velocity;
+    int d = of_ge(position, p->goal_position) && of_ge(velocity, p->goal_velocity);
     double r = -1.0;
 
     /* :425 */
@@ -364,6 +384,13 @@ void orc_pendulum_new(orc_pendulum_env *env)
     env->state[1] = 0.;
 }
 
+/* numpy.clip, which upstream Gym's pendulum.py uses (NaN propagates) */
+static double np_clip(double v, double lo, double hi)
+{
+    if (v != v) return v;
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
 /* ((x + pi) mod 2 pi) - pi with a floor-mod (result in [-pi, pi)) */
 double orc_angle_normalize(double x)
 {
@@ -380,12 +407,12 @@ int orc_pendulum_step(orc_pendulum_env *env, double action, double obs[3],
     double th = env->state[0];
     double thdot = env->state[1];
 
-    double u = orc_clip(action, -p->max_torque, p->max_torque);
+    double u = np_clip(action, -p->max_torque, p->max_torque);
     double an = orc_angle_normalize(th);
     double costs = an * an + 0.1 * (thdot * thdot) + 0.001 * (u * u);
 
     double newthdot = thdot + (3. * p->g / (2. * p->l) * sin(th) + 3.0 / (p->m * (p->l * p->l)) * u) * p->dt;
-    newthdot = orc_clip(newthdot, -p->max_speed, p->max_speed);
+    newthdot = np_clip(newthdot, -p->max_speed, p->max_speed);
     double newth = th + newthdot * p->dt;
 
     env->state[0] = newth;

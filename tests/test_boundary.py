@@ -146,3 +146,11 @@ def test_module_paths_follow_the_crate():
     o = CartPoleObservation(1.0, 2.0, 3.0, 4.0)
     assert (-o).to_vec() == [-1.0, -2.0, -3.0, -4.0]
     assert gym_rs_b200.RenderMode.NONE.value == "none"
+
+
+def test_clip_uses_ordered_float_total_order():
+    """O64 = OrderedFloat<f64> (types.rs:4): NaN sorts above everything, so clip(NaN) is the right bound."""
+    from gym_rs_b200.utils.custom.util_fns import clip
+    nan = float("nan")
+    assert clip(nan, -0.07, 0.07) == 0.07
+    assert clip(float("inf"), -1.0, 2.0) == 2.0 and clip(float("-inf"), -1.0, 2.0) == -1.0

@@ -257,3 +257,21 @@ def test_bench_rollout_runs():
     assert t > 0 and cs < 0
     t, cs = oracle.bench_rollout(oracle.PENDULUM, 4096, 20, 2, 1, seed=0)
     assert t > 0 and math.isfinite(cs)
+
+
+# ---- OrderedFloat total-order semantics (O64 = OrderedFloat<f64>, types.rs:4) ------------
+
+def test_nan_follows_ordered_float_total_order():
+    """The reference compares OrderedFloat values: NaN == NaN and NaN is greater than everything.
+    So clip(NaN) is the RIGHT bound (util_fns.rs:2-10) and a NaN cart position / pole angle is
+    'greater than the threshold', i.e. done (cartpole.rs:450-453)."""
+    L = oracle.lib()
+    nan = float("nan")
+    assert L.orc_clip(nan, -0.07, 0.07) == 0.07
+    assert L.orc_clip(math.inf, -0.07, 0.07) == 0.07 and L.orc_clip(-math.inf, -0.07, 0.07) == -0.07
+    st = np.array([[nan, 0.0, 0.0], [0.0, 0.0, 0.0], [0.0, nan, 0.0], [0.0, 0.0, 0.0]])
+    r = oracle.step_batch(oracle.CARTPOLE, st, [1, 1, 1])
+    assert list(r["done"]) == [1, 1, 0]
+    # MountainCar: a NaN position makes cos() NaN -> velocity clipped to +max_speed, position to max_position
+    r = oracle.step_batch(oracle.MOUNTAIN_CAR, np.array([[nan], [0.0]]), [1])
+    assert r["state"][0, 0] == 0.6 and r["state"][1, 0] == 0.07 and r["done"][0] == 1

@@ -203,6 +203,52 @@ def test_mutated_pub_fields_take_effect(torch, g):
     env.close()
 
 
+def test_special_values_follow_the_reference_semantics(torch, g):
+    """Large angles (full-range sincosf path), huge velocities, infinities and NaN.  The reference
+    compares OrderedFloat values (NaN greater than everything): a NaN cart/pole is done, and
+    MountainCar clips a NaN to the RIGHT bound (util_fns.rs:2-10)."""
+    nan, inf = float("nan"), float("inf")
+    st = np.array([
+        # x       x_dot   theta    theta_dot
+        [0.0,     0.0,    1.0,     0.0],      # beyond pi/4: sincosf path
+        [0.0,     0.0,    -3.0,    2.0],
+        [1.0,     -1.0,   1.0e4,   0.5],      # needs the full range reduction
+        [0.0,     0.0,    0.1,     1.0e3],    # theta_dot^2 = 1e6
+        [1.0e6,   10.0,   0.0,     0.0],
+        [nan,     0.0,    0.0,     0.0],
+        [0.0,     0.0,    nan,     0.0],
+        [inf,     0.0,    0.0,     0.0],
+        [0.0,     nan,    0.0,     0.0],      # NaN velocity: x becomes NaN after the Euler update
+    ], dtype=np.float32).T
+    act = np.array([1, 0, 1, 0, 1, 1, 0, 1, 0], dtype=np.int32)
+    env = g.CartPoleEnv(num_envs=st.shape[1])
+    env.set_state(st)
+    out = env.step(dev_actions(torch, act))
+    env.sync()
+    ref = oracle.step_batch(oracle.CARTPOLE, st, act)
+    got = out.observation.cpu().numpy()
+    fin = np.isfinite(ref["state"])
+    assert np.array_equal(np.isnan(got), np.isnan(ref["state"]))
+    assert np.array_equal(np.isinf(got), np.isinf(ref["state"]))
+    assert_within(np.where(fin, got, 0.0), np.where(fin, ref["state"], 0.0), "special values", tol=2e-6)
+    assert np.array_equal(out.done.cpu().numpy(), ref["done"])
+    assert ref["done"][5] == 1 and ref["done"][6] == 1 and ref["done"][8] == 1  # NaN is "greater than" the threshold
+    env.close()
+
+    st = np.array([[nan, 0.0], [0.0, nan], [inf, 0.0], [-inf, 0.0], [0.0, inf]], dtype=np.float32).T
+    act = np.array([1, 1, 2, 0, 1], dtype=np.int32)
+    env = g.MountainCarEnv(num_envs=st.shape[1])
+    env.set_state(st)
+    out = env.step(dev_actions(torch, act))
+    env.sync()
+    ref = oracle.step_batch(oracle.MOUNTAIN_CAR, st, act)
+    got = out.observation.cpu().numpy()
+    assert np.isfinite(got).all() and np.isfinite(ref["state"]).all()
+    assert_within(got, ref["state"], "mountain car special values")
+    assert np.array_equal(out.done.cpu().numpy(), ref["done"])
+    env.close()
+
+
 # --------------------------------------------------------------------------------------
 # golden vectors (tests/golden/step_vectors.json) through the GPU
 # --------------------------------------------------------------------------------------
