@@ -61,11 +61,11 @@ float f32_ceil(double v)
 void make_reset_box(ResetBox &rb, int dim, const float *low, const float *high)
 {
     for (int i = 0; i < 4; ++i) {
-        rb.low[i] = 0.f; rb.scale[i] = 0.f; rb.cap[i] = 0.f;
+        rb.low[i] = 0.f; rb.scale24[i] = 0.f; rb.cap[i] = 0.f;
     }
     for (int i = 0; i < dim; ++i) {
         rb.low[i] = low[i];
-        rb.scale[i] = high[i] - low[i];
+        rb.scale24[i] = (high[i] - low[i]) * 5.9604644775390625e-08f; // * 2^-24, exact
         rb.cap[i] = high[i] > low[i] ? std::nextafterf(high[i], low[i]) : low[i];
     }
 }
@@ -199,7 +199,7 @@ BatchArgs base_args(const gymrs_env *e)
     a.max_steps = max_episode_steps(e);
     a.n = e->n;
     a.global_off = e->global_off;
-    a.seed = e->seed;
+    a.rk = philox_round_keys(e->seed);
     a.epoch = e->step_count + 1;
     a.err = e->err_dev;
     a.chain_flags = e->chain_mem + 1;
@@ -565,7 +565,7 @@ int gymrs_reset(gymrs_env *e, const uint64_t *seed, const float *low, const floa
     std::memcpy(e->reset_high, hi, sizeof hi);
     fold_params(e);
     BatchArgs a = base_args(e);
-    a.seed = s;
+    a.rk = philox_round_keys(s);
     e->chain_ok = false;
     cudaError_t ce = do_reset(e, a, mask, e->stream);
     std::memcpy(e->reset_low, keep_lo, sizeof keep_lo);

@@ -24,7 +24,7 @@ namespace gymrs {
 
 struct ResetBox {
     float low[4];   // lower bound per state row
-    float scale[4]; // high - low
+    float scale24[4]; // (high - low) * 2^-24: maps the 24 random bits straight onto [low, high)
     float cap[4];   // largest float below high
 };
 
@@ -121,10 +121,10 @@ struct CartPole {
     // four iid uniforms in the order x, x_dot, theta, theta_dot                      :317-324
     __device__ __forceinline__ static void reset(const P &p, float (&s)[SD], float (&)[OD], uint4 w)
     {
-        s[0] = uniform_from_word(w.x, p.rb.low[0], p.rb.scale[0], p.rb.cap[0]);
-        s[1] = uniform_from_word(w.y, p.rb.low[1], p.rb.scale[1], p.rb.cap[1]);
-        s[2] = uniform_from_word(w.z, p.rb.low[2], p.rb.scale[2], p.rb.cap[2]);
-        s[3] = uniform_from_word(w.w, p.rb.low[3], p.rb.scale[3], p.rb.cap[3]);
+        s[0] = uniform_from_word(w.x, p.rb.low[0], p.rb.scale24[0], p.rb.cap[0]);
+        s[1] = uniform_from_word(w.y, p.rb.low[1], p.rb.scale24[1], p.rb.cap[1]);
+        s[2] = uniform_from_word(w.z, p.rb.low[2], p.rb.scale24[2], p.rb.cap[2]);
+        s[3] = uniform_from_word(w.w, p.rb.low[3], p.rb.scale24[3], p.rb.cap[3]);
     }
 };
 
@@ -178,7 +178,7 @@ struct MountainCar {
 
     __device__ __forceinline__ static void reset(const P &p, float (&s)[SD], float (&)[OD], uint4 w)
     {
-        s[0] = uniform_from_word(w.x, p.rb.low[0], p.rb.scale[0], p.rb.cap[0]);
+        s[0] = uniform_from_word(w.x, p.rb.low[0], p.rb.scale24[0], p.rb.cap[0]);
         s[1] = 0.0f;
     }
 };
@@ -235,8 +235,8 @@ struct Pendulum {
 
     __device__ __forceinline__ static void reset(const P &p, float (&s)[SD], float (&o)[OD], uint4 w)
     {
-        s[0] = uniform_from_word(w.x, p.rb.low[0], p.rb.scale[0], p.rb.cap[0]);
-        s[1] = uniform_from_word(w.y, p.rb.low[1], p.rb.scale[1], p.rb.cap[1]);
+        s[0] = uniform_from_word(w.x, p.rb.low[0], p.rb.scale24[0], p.rb.cap[0]);
+        s[1] = uniform_from_word(w.y, p.rb.low[1], p.rb.scale24[1], p.rb.cap[1]);
         float sn, cs;
         sincosf(s[0], &sn, &cs);
         o[0] = cs; o[1] = sn; o[2] = s[1];

@@ -24,7 +24,7 @@ struct BatchArgs {
     uint32_t max_steps;  // TIME_LIMIT horizon
     uint64_t n;          // envs in this launch
     uint64_t global_off; // global id of env 0
-    uint64_t seed;       // Philox key
+    PhiloxKeys rk;       // Philox round keys of the handle's seed (philox_round_keys)
     uint64_t epoch;      // Philox counter high half for auto-resets in this step (rollout: first step)
     uint32_t *err;       // device-visible words: [0] invalid-action flag, [1..2] one offending global id,
                          // [3] chained-dependency timeout flag

@@ -184,7 +184,7 @@ __device__ __forceinline__ void transition(const typename E::P &p, const BatchAr
             const int j = __ffs(need_reset) - 1;
             need_reset &= need_reset - 1;
             float sj[E::SD], oj[E::OD];
-            E::reset(p, sj, oj, reset_words(a.seed, gid0 + j, epoch));
+            E::reset(p, sj, oj, reset_words(a.rk, gid0 + j, epoch));
 #pragma unroll
             for (int jj = 0; jj < V; ++jj) {
                 if (jj == j) {
@@ -567,7 +567,7 @@ reset_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Ba
     if (i >= a.n) return;
     if (mask && !mask[i]) return;
     float s[E::SD], o[E::OD];
-    E::reset(p, s, o, reset_words(a.seed, a.global_off + i, 0));
+    E::reset(p, s, o, reset_words(a.rk, a.global_off + i, 0));
 #pragma unroll
     for (int r = 0; r < E::SD; ++r) a.state[r * a.ld + i] = s[r];
     if (!E::OBS_IS_STATE) {

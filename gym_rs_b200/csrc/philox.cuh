@@ -13,35 +13,52 @@
 
 namespace gymrs {
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+// The ten round keys (k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85).  The key is the seed, the same
+// for every env of a launch, so the host expands it once (philox_round_keys) and the kernel reads
+// the schedule from its parameter block instead of re-deriving it per reset.
+struct PhiloxKeys {
+    uint32_t k[10][2];
+};
+
+inline PhiloxKeys philox_round_keys(uint64_t seed)
+{
+    PhiloxKeys rk;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        rk.k[r][0] = k0;
+        rk.k[r][1] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return rk;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &rk)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
+        c = make_uint4(hi1 ^ c.y ^ rk.k[r][0], lo1, hi0 ^ c.w ^ rk.k[r][1], lo0);
     }
     return c;
 }
 
 // The four words that env `gid` draws at `epoch` (0 = explicit reset,
 // 1 + step index = auto-reset during that step).
-__device__ __forceinline__ uint4 reset_words(uint64_t seed, uint64_t gid, uint64_t epoch)
+__device__ __forceinline__ uint4 reset_words(const PhiloxKeys &rk, uint64_t gid, uint64_t epoch)
 {
     return philox4x32_10(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32),
-                                    (uint32_t)epoch, (uint32_t)(epoch >> 32)),
-                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+                                    (uint32_t)epoch, (uint32_t)(epoch >> 32)), rk);
 }
 
 // U[low, low + scale) on a 2^-24 grid: the reference draws from the half-open
-// range (rand Uniform::new, cartpole.rs:363, mountain_car.rs:189).  `cap` is the
-// largest float below high, so rounding in the fma can never return high itself.
-__device__ __forceinline__ float uniform_from_word(uint32_t w, float low, float scale, float cap)
+// range (rand Uniform::new, cartpole.rs:363, mountain_car.rs:189).  scale24 = scale * 2^-24
+// (exact), so this is low + (w >> 8) * 2^-24 * scale in one FMA.  `cap` is the largest float
+// below high, so rounding in the fma can never return high itself.
+__device__ __forceinline__ float uniform_from_word(uint32_t w, float low, float scale24, float cap)
 {
-    const float r = (float)(w >> 8) * 5.9604644775390625e-08f; // 2^-24
-    return fminf(fmaf(r, scale, low), cap);
+    return fminf(fmaf((float)(w >> 8), scale24, low), cap);
 }
 
 } // namespace gymrs
