@@ -407,11 +407,27 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             rms = float(t.item())
         rbytes = ROLLOUT_BYTES[env] + 2 * 4 * e0.state_dim / kr
+        wbytes = ROLLOUT_BYTES[env] - 4 + 4 * e0.state_dim / kr  # everything but the action row is a WRITE
+        # The rollout is ~85 % writes, and write-only HBM traffic has a lower ceiling than the copy
+        # the roofline peak is measured with: measure that ceiling here (1 GiB fill, best of 5).
+        probe = torch.empty(1 << 30, dtype=torch.uint8, device=device)
+        fill_ms = []
+        for _ in range(5):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            probe.fill_(1)
+            ev1.record(stream)
+            torch.cuda.synchronize(device)
+            fill_ms.append(ev0.elapsed_time(ev1))
+        write_peak = (1 << 30) / (min(fill_ms) * 1e-3) / 1e9
+        del probe
         rollout = {"value": world * n * kr / (rms * 1e-3), "unit": "env-steps/s", "steps_per_launch": kr,
                    "ms_per_launch": rms, "algorithmic_bytes_per_env_step": rbytes,
                    "achieved_gbs": rbytes * n * kr / (rms * 1e-3) / 1e9, "frac": rbytes * n * kr / (rms * 1e-3) / 1e9 / peak,
+                   "write_gbs": wbytes * n * kr / (rms * 1e-3) / 1e9, "hbm_write_only_gbs_measured": write_peak,
                    "api": "gymrs_rollout: one launch, state in registers, actions in / obs, reward, done out per step "
-                          f"({kr * (ROLLOUT_BYTES[env]) * n / 1e6:.0f} MB streamed per launch, larger than L2)"}
+                          f"({kr * (ROLLOUT_BYTES[env]) * n / 1e6:.0f} MB streamed per launch, larger than L2); "
+                          "write-dominated, so its ceiling is the write-only HBM rate, not the copy rate `frac` uses"}
         del acts, obs_out, rew_out, done_out
 
     cpu = None
