@@ -685,9 +685,11 @@ int gymrs_host_wait(gymrs_env *e, uint64_t ticket)
 {
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
     if (ticket >= e->host_seq) return fail(GYMRS_ERR_BAD_ARG, "unknown ticket");
-    if (e->hev.empty() || ticket + 2 < e->host_seq) return GYMRS_OK; // its event slot was re-recorded by a later, waited step
+    if (e->hev.empty()) return GYMRS_OK;
     CU(cudaSetDevice(e->device));
-    // a slot re-recorded by ticket + 2 can only make this wait longer, never shorter
+    // The event slot is shared by tickets of the same parity.  If a later step re-recorded it,
+    // that record sits behind this ticket's copies on the same in-order stream, so waiting for
+    // it can only be longer, never shorter.
     CU(cudaEventSynchronize(e->hev[HostEv::host_done((int)(ticket & 1))]));
     if (ticket + 1 == e->host_seq) {
         // newest host step: nothing of it is in flight any more

@@ -714,6 +714,44 @@ def test_sharding_invariance_at_full_size(torch, g):
         e.close()
 
 
+def test_mirror_symmetry_at_full_size(torch, g):
+    """Size-independent property at BASELINE's full size: CartPole's dynamics are odd under
+    (state, force) -> (-state, -force).  Every operation on the device path (polynomial sin/cos,
+    FMA chain, reciprocal + Newton step, |x| > T tests) is sign-symmetric, so stepping the mirrored
+    batch must give the exactly negated state and identical done flags -- for all 2^20 envs, over
+    several steps, with no oracle involved."""
+    n = N_FULL
+    st, act = cartpole_inputs(n, seed=13)
+    a = g.CartPoleEnv(num_envs=n)
+    b = g.CartPoleEnv(num_envs=n)
+    a.set_state(st)
+    b.set_state(-st)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    for _ in range(12):
+        acts = torch.randint(0, 2, (n,), generator=gen, device="cuda", dtype=torch.int32)
+        oa = a.step(acts)
+        ob = b.step(1 - acts)
+    a.sync()
+    b.sync()
+    assert torch.equal(oa.observation, -ob.observation)
+    assert torch.equal(oa.done, ob.done) and torch.equal(oa.reward, ob.reward)
+    assert torch.equal(a.steps_beyond_terminated, b.steps_beyond_terminated)
+    a.close()
+    b.close()
+    # MountainCar: outputs stay inside the observation space for arbitrary inputs (clip, mountain_car.rs:413-416)
+    m = g.MountainCarEnv(num_envs=n)
+    wild = np.stack([np.random.default_rng(1).uniform(-5, 5, n), np.random.default_rng(2).uniform(-1, 1, n)])
+    m.set_state(wild.astype(np.float32))
+    out = m.step(torch.randint(0, 3, (n,), generator=gen, device="cuda", dtype=torch.int32))
+    m.sync()
+    o = out.observation
+    assert float(o[0].min()) >= np.float32(-1.2) and float(o[0].max()) <= np.float32(0.6)
+    assert float(o[1].abs().max()) <= np.float32(0.07)
+    assert bool(((o[0] > np.float32(-1.2)) | (o[1] >= 0)).all())        # wall rule
+    assert torch.equal(out.done.bool(), (o[0] >= 0.5) & (o[1] >= 0))
+    m.close()
+
+
 def test_determinism_same_seed_same_bits(torch, g):
     n = 1 << 18
     gen = torch.Generator(device="cuda").manual_seed(4)
