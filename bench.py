@@ -104,7 +104,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.005)
 
     def __enter__(self):
         if self.ok:
@@ -303,7 +303,9 @@ def run_b200(args):
     barrier()
     # the timed region: EXACTLY K steps; repeated so the clock sampler sees sustained load, median reported
     est = timed(K, handles)
-    repeats = int(min(25, max(3, 600.0 / max(est, 1e-3))))
+    # enough repeats for ~0.4 s under load (so that the 5 ms clock sampler sees it) whatever K is,
+    # but no more than ~2 s worth; at the default K that is ~25 repeats
+    repeats = int(min(2000, max(3, 400.0 / max(est, 1e-3))))
     with ClockSampler(local_rank) as cs:
         times = [timed(K, handles) for _ in range(repeats)]
     clocks = cs.summary()
@@ -468,7 +470,8 @@ def run_b200(args):
                             "ms_per_step": ms_res / K,
                             "note": "ONE 1M-env batch stepped back to back on one stream, pdl=2 (a true dependency "
                                     "chain; the state stays in the 126 MB L2); not an HBM number"},
-            "all_ms_per_step": [t / K for t in times],
+            "all_ms_per_step": [t / K for t in times][:40],
+            "ms_per_step_min_max": [min(times) / K, max(times) / K],
         }
         print(json.dumps(line), flush=True)
     for e, _ in ring:
