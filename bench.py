@@ -434,7 +434,10 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, t, cores, sample, _ = cpu_rollout(env, n, 40, 3, budget_s=20.0)
+        # bounded sample: 400 steps of the full 1M-env batch is ~1-2 s of wall time on 16 cores,
+        # i.e. ~15-30 core-seconds of CPU work; cpu_rollout shrinks the batch if a slower host
+        # would exceed the 20 s wall budget
+        v, t, cores, sample, _ = cpu_rollout(env, n, 400, 5, budget_s=20.0)
         cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
