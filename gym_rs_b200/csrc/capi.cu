@@ -43,6 +43,26 @@ int cuda_fail(cudaError_t e, const char *what)
         if (e_ != cudaSuccess) return cuda_fail(e_, #expr);             \
     } while (0)
 
+// Makes `device` current for the rest of the enclosing scope and restores the caller's device on
+// exit: a library must not change the calling thread's current device behind its back.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1; // already current: nothing to restore
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define ON_DEVICE(dev)                                                  \
+    DeviceGuard device_guard_(dev);                                     \
+    if (device_guard_.err != cudaSuccess) return cuda_fail(device_guard_.err, "cudaSetDevice")
+
 // largest float <= v  /  smallest float >= v: lets a float compare against a double
 // threshold be decided exactly ((x > T) == (x > f32_floor(T)) for every float x).
 float f32_floor(double v)
@@ -120,7 +140,6 @@ struct gymrs_env {
     uint64_t seed = 0;       // Philox key of the auto-reset stream
     uint64_t step_count = 0; // steps since the last full reset; epoch of an auto-reset = step_count + 1
     bool sbt_dirty = false;  // some env may hold steps_beyond_terminated = Some(_)
-    int sticky = 0;
     int vec = 0, block = 0, pdl = 1;
 };
 
@@ -285,7 +304,7 @@ void after_step(gymrs_env *e, uint32_t step_flags, uint32_t n_steps)
 int free_env(gymrs_env *e)
 {
     if (!e) return GYMRS_OK;
-    cudaSetDevice(e->device);
+    DeviceGuard device_guard_(e->device);
     for (auto &s : e->copy_streams) if (s) cudaStreamSynchronize(s);
     if (e->own_stream) cudaStreamSynchronize(e->own_stream);
     cudaFree(e->state);
@@ -310,7 +329,7 @@ int alloc_env(gymrs_env *e)
     const uint64_t n = e->n;
     e->ld = (n + 127) / 128 * 128; // rows start 512-byte aligned
     if (e->ld == 0) e->ld = 128;
-    CU(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
     for (auto &s : e->copy_streams) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -455,6 +474,7 @@ int gymrs_clone(const gymrs_env *src, gymrs_env **out)
 {
     if (!src || !out) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     *out = nullptr;
+    ON_DEVICE(src->device);
     gymrs_env *e = new (std::nothrow) gymrs_env();
     if (!e) return fail(GYMRS_ERR_ALLOC, "host allocation failed");
     e->kind = src->kind; e->n = src->n; e->device = src->device; e->global_off = src->global_off;
@@ -515,7 +535,7 @@ int gymrs_get_params(const gymrs_env *e, void *params)
 int gymrs_set_stream(gymrs_env *e, void *cuda_stream)
 {
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
-    CU(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
     CU(cudaStreamSynchronize(e->stream));
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
@@ -545,7 +565,7 @@ int gymrs_reset(gymrs_env *e, const uint64_t *seed, const float *low, const floa
 {
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
     if ((low == nullptr) != (high == nullptr)) return fail(GYMRS_ERR_BAD_ARG, "low and high must be given together");
-    CU(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
     const uint64_t s = seed ? *seed : entropy64(); // seeding.rs:22
     if (seed_used) *seed_used = s;
@@ -583,7 +603,7 @@ int gymrs_reset(gymrs_env *e, const uint64_t *seed, const float *low, const floa
 int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
 {
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
-    CU(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
     BatchArgs a = base_args(e);
     a.actions = actions;
@@ -616,7 +636,7 @@ int gymrs_step_host_async(gymrs_env *e, const void *actions, uint32_t step_flags
                           float *obs, float *reward, uint8_t *done, uint8_t *truncated, uint64_t *ticket)
 {
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
-    CU(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     const uint64_t n = e->n;
     const uint64_t tk = e->host_seq;
     const int par = (int)(tk & 1);
@@ -686,7 +706,7 @@ int gymrs_host_wait(gymrs_env *e, uint64_t ticket)
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
     if (ticket >= e->host_seq) return fail(GYMRS_ERR_BAD_ARG, "unknown ticket");
     if (e->hev.empty()) return GYMRS_OK;
-    CU(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     // The event slot is shared by tickets of the same parity.  If a later step re-recorded it,
     // that record sits behind this ticket's copies on the same in-order stream, so waiting for
     // it can only be longer, never shorter.
@@ -707,6 +727,7 @@ int gymrs_step_host(gymrs_env *e, const void *actions, uint32_t step_flags,
     if (rc != GYMRS_OK) return rc;
     rc = gymrs_host_wait(e, ticket);
     if (rc != GYMRS_OK) return rc;
+    ON_DEVICE(e->device);
     CU(cudaStreamSynchronize(e->stream));
     return GYMRS_OK;
 }
@@ -716,7 +737,7 @@ int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t 
 {
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     if (n_steps == 0) return GYMRS_OK;
-    CU(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
     BatchArgs a = base_args(e);
     a.actions = actions;
@@ -735,7 +756,7 @@ int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t 
 int gymrs_get_state(gymrs_env *e, float *state, int32_t *sbt)
 {
     if (!e || !state) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
-    CU(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
     CU(cudaMemcpy2DAsync(state, sizeof(float) * e->n, e->state, sizeof(float) * e->ld,
                          sizeof(float) * e->n, e->state_dim, cudaMemcpyDeviceToHost, e->stream));
@@ -750,7 +771,7 @@ int gymrs_get_state(gymrs_env *e, float *state, int32_t *sbt)
 int gymrs_set_state(gymrs_env *e, const float *state, const int32_t *sbt)
 {
     if (!e || !state) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
-    CU(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
     e->chain_ok = false;
     CU(cudaMemcpy2DAsync(e->state, sizeof(float) * e->ld, state, sizeof(float) * e->n,
@@ -847,7 +868,7 @@ int gymrs_kind_of(const gymrs_env *e, int *kind)
 int gymrs_sync(gymrs_env *e, uint64_t *bad_env)
 {
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
-    CU(cudaSetDevice(e->device));
+    ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
     CU(cudaStreamSynchronize(e->stream));
     if (e->err_host[3]) {

@@ -54,3 +54,38 @@ def test_two_rank_shards_equal_single_gpu(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29581", str(script)],
                        capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_one_process_drives_two_devices_without_disturbing_the_current_device():
+    """SURVEY.md section 8e allows 'one process driving several devices': handles on different GPUs in
+    one process; every C-ABI call must leave the caller's current CUDA device untouched."""
+    import numpy as np
+    import torch
+
+    import gym_rs_b200 as g
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    torch.cuda.set_device(0)
+    n = 1 << 16
+    e0 = g.CartPoleEnv(num_envs=n, device=0, global_env_offset=0)
+    e1 = g.CartPoleEnv(num_envs=n, device=1, global_env_offset=n)
+    assert torch.cuda.current_device() == 0
+    whole = g.CartPoleEnv(num_envs=2 * n, device=0)
+    for e in (e0, e1, whole):
+        e.reset(seed=3)
+    acts = torch.randint(0, 2, (2 * n,), device="cuda:0", dtype=torch.int32)
+    a1 = acts[n:].to("cuda:1")
+    torch.cuda.synchronize(0)
+    torch.cuda.synchronize(1)
+    for _ in range(20):
+        e0.step(acts[:n].contiguous(), autoreset=True)
+        e1.step(a1, autoreset=True)
+        whole.step(acts, autoreset=True)
+        assert torch.cuda.current_device() == 0
+    for e in (e0, e1, whole):
+        e.sync()
+    s = whole.get_state()
+    assert np.array_equal(s[:, :n], e0.get_state()) and np.array_equal(s[:, n:], e1.get_state())
+    assert torch.cuda.current_device() == 0
+    for e in (e0, e1, whole):
+        e.close()
