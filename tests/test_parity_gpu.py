@@ -523,7 +523,9 @@ def test_vec_widths_and_ragged_sizes_are_bit_identical(torch, g, kind):
 
 
 @pytest.mark.parametrize("kind,n,vec,block", [("cartpole", N_FULL, 0, 0), ("cartpole", 300001, 1, 32),
-                                              ("mountain_car", 1 << 19, 2, 64), ("pendulum", 777777, 4, 128)])
+                                              ("mountain_car", 1 << 19, 2, 64), ("pendulum", 777777, 4, 128),
+                                              # vec = 8: the persistent TMA-staged kernel (ragged last tile included)
+                                              ("cartpole", N_FULL + 516, 8, 0), ("pendulum", 1 << 18, 8, 0)])
 def test_chained_pdl_launches_match_plain_launches(torch, g, kind, n, vec, block):
     """pdl = 2 pipelines back-to-back steps: a CTA waits only for the same-index CTA of the handle's
     previous step (per-CTA release/acquire flags) instead of the whole previous grid.  Results must
@@ -537,10 +539,13 @@ def test_chained_pdl_launches_match_plain_launches(torch, g, kind, n, vec, block
         acts = [torch.randint(0, 2, (n,), generator=gen, device="cuda", dtype=torch.int32) for _ in range(8)]
     torch.cuda.synchronize()
     finals = {}
-    for pdl in (0, 2):
+    # (launch width, pdl): plain vs chained launches of the same kernel; for the TMA-staged kernel
+    # (vec = 8) additionally the plain step_kernel, which must give the same bits
+    configs = [(vec, 0), (vec, 2)] + ([(4, 1)] if vec == 8 else [])
+    for cfg_vec, pdl in configs:
         envs = [cls(num_envs=n, global_env_offset=k * n) for k in range(3)]
         for e in envs:
-            e.set_launch_config(vec=vec, block=block, pdl=pdl)
+            e.set_launch_config(vec=cfg_vec, block=block, pdl=pdl)
             e.reset(seed=11)
         for t in range(240):
             for k, e in enumerate(envs):  # three handles interleaved on one stream
@@ -552,12 +557,14 @@ def test_chained_pdl_launches_match_plain_launches(torch, g, kind, n, vec, block
                 envs[2].rollout(torch.stack(acts[:2]), autoreset=True)
         for e in envs:
             e.sync()
-        finals[pdl] = [(e.get_state(), e._t_reward.cpu().numpy(), e._t_done.cpu().numpy()) for e in envs]
+        finals[(cfg_vec, pdl)] = [(e.get_state(), e._t_reward.cpu().numpy(), e._t_done.cpu().numpy()) for e in envs]
         for e in envs:
             e.close()
-    for a, b in zip(finals[0], finals[2]):
-        for x, y in zip(a, b):
-            assert np.array_equal(x, y)
+    base = finals[configs[0]]
+    for cfg in configs[1:]:
+        for a, b in zip(base, finals[cfg]):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), cfg
 
 
 def test_unaligned_action_pointer_falls_back_to_scalar_lanes(torch, g):
