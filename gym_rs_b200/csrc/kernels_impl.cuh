@@ -300,29 +300,32 @@ step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Bat
 }
 
 // ---- step, persistent TMA-staged stream ------------------------------------------
-// Same transition, different data movement.  The grid is persistent: G = (#SMs x CTAs per SM)
-// CTAs, CTA c walks the tiles c, c + G, c + 2G, ... of 1024 envs.  Each CTA keeps a ring of
-// STREAM_STAGES tiles in shared memory: one thread issues a bulk async copy (cp.async.bulk, the
-// 1-D TMA path -- UBLKCP in SASS) per input row of a tile, completing on that stage's mbarrier,
-// while the 256 threads consume the previous tile with conflict-free LDS.128 and store results
-// straight to global.  Compared with step_kernel this
-//   * always has a tile in flight per CTA, held in shared memory instead of registers, so the
+// Same transition, different data movement (opt-in: launch config vec = 8).  The grid is
+// persistent: G = (#SMs x CTAs per SM) CTAs, CTA c walks the tiles c, c + G, c + 2G, ... of 1024
+// envs.  Each CTA keeps a ring of STREAM_STAGES tiles in shared memory: its control warp issues a
+// bulk async copy (cp.async.bulk, the 1-D TMA path -- UBLKCP in SASS) per input row of a tile,
+// completing on that stage's `full` mbarrier, while the 8 compute warps consume landed tiles with
+// conflict-free LDS.128 and store results straight to global.  Compared with step_kernel this
+//   * always has tiles in flight per CTA, held in shared memory instead of registers, so the
 //     bytes in flight per SM no longer depend on how many register-heavy CTAs fit,
 //   * occupies only part of each SM, so with PDL the next launch's CTAs are co-resident from the
 //     start and stream in right behind (its trigger fires immediately: the grid is one wave),
-//   * replaces per-thread 64-bit address arithmetic + LDG by one LDS per row.
+//   * replaces per-thread 64-bit address arithmetic + LDG by one LDS per row,
+//   * keeps flag waits and the release fence of chained launches off the compute warps.
 // Chained-launch flags are per tile (1024 envs), the same granularity as step_kernel<V = 4> with
-// 256-thread CTAs, so the two kernels can follow each other in a chain.
+// 256-thread CTAs, so the two kernels can follow each other in a chain.  Measured:
+// a little faster than step_kernel for chained launches on one stream, slower when the batch is
+// L2-resident (a tile is worked on by only 8 warps) -- hence opt-in.
 constexpr int TMA_TILE = 1024; // envs per tile = 256 threads x 4
 #ifndef GYMRS_STREAM_STAGES
-#define GYMRS_STREAM_STAGES 2
+#define GYMRS_STREAM_STAGES 3
 #endif
 constexpr int STREAM_STAGES = GYMRS_STREAM_STAGES;
 
 template <class E, bool SBT, bool TL>
 struct TmaCfg {
     static constexpr int ROWS = E::SD + 1 + (SBT ? 1 : 0) + (TL ? 1 : 0); // state rows, action row, optional rows
-    static constexpr size_t SMEM = (size_t)STREAM_STAGES * ROWS * TMA_TILE * 4 + STREAM_STAGES * 8;
+    static constexpr size_t SMEM = (size_t)STREAM_STAGES * ROWS * TMA_TILE * 4 + 2 * STREAM_STAGES * 8; // + full/done mbarriers
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -368,11 +371,23 @@ __device__ __forceinline__ void chain_wait(const BatchArgs &a, uint64_t t, uint3
 }
 
 #ifndef GYMRS_STREAM_MIN_CTAS
-#define GYMRS_STREAM_MIN_CTAS 5
+#define GYMRS_STREAM_MIN_CTAS 4
 #endif
+constexpr int STREAM_COMPUTE_THREADS = 256;                      // 8 warps, 4 envs per thread = one tile
+constexpr int STREAM_THREADS = STREAM_COMPUTE_THREADS + 32;      // + one control warp
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised: warps 0-7 compute, warp 8 (one lane) is the control warp that owns every
+// inter-CTA duty -- waiting on the previous step's tile flags, issuing the bulk copies, and
+// publishing finished tiles with a release store.  The release fence and the flag spins therefore
+// never stall a compute warp; compute warps only wait on the stage's `full` mbarrier and signal
+// `done` (256 arrivals) when they have read the stage and issued their stores.
 template <class E, bool AR, bool SBT, bool TL>
-__global__ void __launch_bounds__(256, GYMRS_STREAM_MIN_CTAS)
+__global__ void __launch_bounds__(STREAM_THREADS, GYMRS_STREAM_MIN_CTAS)
 step_stream_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ BatchArgs a)
 {
     using A = typename E::Action;
@@ -382,6 +397,7 @@ step_stream_kernel(const __grid_constant__ typename E::P p, const __grid_constan
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float(*tile)[ROWS][TMA_TILE] = reinterpret_cast<float(*)[ROWS][TMA_TILE]>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * ROWS * TMA_TILE * 4);
+    uint64_t *done = full + S;
 
     const uint64_t ntiles = (a.n + TMA_TILE - 1) / TMA_TILE;
     const uint64_t G = gridDim.x;
@@ -392,39 +408,43 @@ step_stream_kernel(const __grid_constant__ typename E::P p, const __grid_constan
         const uint64_t left = a.n - t * TMA_TILE;
         return left < (uint64_t)TMA_TILE ? (uint32_t)left : (uint32_t)TMA_TILE;
     };
-    // thread 0 only: arm the stage's barrier and (optionally) fetch the action row
-    auto arm = [&](uint32_t k) {
-        const uint64_t t = tile_of(k);
-        const uint32_t bytes = tile_envs(t) * 4u;
-        mbar_expect_tx(&full[k % S], ROWS * bytes);
-        if (a.early_actions)
-            bulk_g2s(tile[k % S][R_ACT], reinterpret_cast<const A *>(a.actions) + t * TMA_TILE, bytes, &full[k % S]);
-    };
-    // thread 0 only: fetch everything the previous step of this handle may have written
-    auto fetch = [&](uint32_t k) {
-        const uint64_t t = tile_of(k), e0 = t * TMA_TILE;
-        const uint32_t bytes = tile_envs(t) * 4u;
-        const int st = k % S;
-#pragma unroll
-        for (int r = 0; r < E::SD; ++r) bulk_g2s(tile[st][r], a.state + r * a.ld + e0, bytes, &full[st]);
-        if (!a.early_actions) bulk_g2s(tile[st][R_ACT], reinterpret_cast<const A *>(a.actions) + e0, bytes, &full[st]);
-        if (SBT) bulk_g2s(tile[st][R_SBT], a.sbt + e0, bytes, &full[st]);
-        if (TL) bulk_g2s(tile[st][R_EL], a.elapsed + e0, bytes, &full[st]);
-    };
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int st = 0; st < S; ++st) mbar_init(&full[st], 1);
+        for (int st = 0; st < S; ++st) {
+            mbar_init(&full[st], 1);
+            mbar_init(&done[st], STREAM_COMPUTE_THREADS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-
-    // prologue: fill the ring
-    const uint32_t K0 = K < (uint32_t)S ? K : (uint32_t)S;
-    if (threadIdx.x == 0)
-        for (uint32_t k = 0; k < K0; ++k) arm(k);
     pdl_launch_dependents();
-    if (threadIdx.x == 0) {
+
+    if (threadIdx.x >= STREAM_COMPUTE_THREADS) {
+        // ------------------------------- control warp -------------------------------
+        if (threadIdx.x != STREAM_COMPUTE_THREADS) return;
+        // arm the stage's barrier and (optionally) fetch the action row
+        auto arm = [&](uint32_t k) {
+            const uint64_t t = tile_of(k);
+            const uint32_t bytes = tile_envs(t) * 4u;
+            mbar_expect_tx(&full[k % S], ROWS * bytes);
+            if (a.early_actions)
+                bulk_g2s(tile[k % S][R_ACT], reinterpret_cast<const A *>(a.actions) + t * TMA_TILE, bytes, &full[k % S]);
+        };
+        // fetch everything the previous step of this handle may have written
+        auto fetch = [&](uint32_t k) {
+            const uint64_t t = tile_of(k), e0 = t * TMA_TILE;
+            const uint32_t bytes = tile_envs(t) * 4u;
+            const int st = k % S;
+#pragma unroll
+            for (int r = 0; r < E::SD; ++r) bulk_g2s(tile[st][r], a.state + r * a.ld + e0, bytes, &full[st]);
+            if (!a.early_actions) bulk_g2s(tile[st][R_ACT], reinterpret_cast<const A *>(a.actions) + e0, bytes, &full[st]);
+            if (SBT) bulk_g2s(tile[st][R_SBT], a.sbt + e0, bytes, &full[st]);
+            if (TL) bulk_g2s(tile[st][R_EL], a.elapsed + e0, bytes, &full[st]);
+        };
+        // prologue: fill the ring
+        const uint32_t K0 = K < (uint32_t)S ? K : (uint32_t)S;
+        for (uint32_t k = 0; k < K0; ++k) arm(k);
         if (a.chain) {
             // per-tile dependency on the same tile of the handle's previous step; the rows were
             // written through the generic proxy and are read below through the async proxy
@@ -434,29 +454,29 @@ step_stream_kernel(const __grid_constant__ typename E::P p, const __grid_constan
             pdl_wait();
         }
         for (uint32_t k = 0; k < K0; ++k) fetch(k);
+        // steady state: when tile k is done, refill its stage, then publish it
+        for (uint32_t k = 0; k < K; ++k) {
+            mbar_wait(&done[k % S], (k / S) & 1u);
+            if (k + S < K) {
+                arm(k + S);
+                if (a.chain) {
+                    chain_wait(a, tile_of(k + S), a.chain_seq - 1u);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                fetch(k + S);
+            }
+            // the mbarrier hand-over orders every compute thread's stores before this release
+            if (a.publish) st_release_gpu(a.chain_flags + tile_of(k), a.chain_seq);
+        }
+        return;
     }
-    // everybody's stores must come after the previous grid when there is no per-tile chain
-    if (!a.chain) pdl_wait();
 
+    // --------------------------------- compute warps ---------------------------------
+    // without a per-tile chain, stores must come after the previous grid has completed
+    if (!a.chain) pdl_wait();
     const uint32_t il = threadIdx.x * V; // first env of this thread inside a tile
 #pragma unroll 1
     for (uint32_t k = 0; k < K; ++k) {
-        if (k > 0) {
-            // every thread has finished tile k - 1 (reads of its stage and all its stores):
-            // publish it and refill its stage with the tile S positions ahead
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                if (a.publish) st_release_gpu(a.chain_flags + tile_of(k - 1), a.chain_seq);
-                if (k - 1 + S < K) {
-                    arm(k - 1 + S);
-                    if (a.chain) {
-                        chain_wait(a, tile_of(k - 1 + S), a.chain_seq - 1u);
-                        asm volatile("fence.proxy.async;" ::: "memory");
-                    }
-                    fetch(k - 1 + S);
-                }
-            }
-        }
         const int st = k % S;
         const uint64_t t = tile_of(k);
         mbar_wait(&full[st], (k / S) & 1u);
@@ -487,10 +507,7 @@ step_stream_kernel(const __grid_constant__ typename E::P p, const __grid_constan
             if (SBT) st_row<V, true>(a.sbt + i0, sbt, V);
             if (TL) st_row<V, true>(a.elapsed + i0, el, V);
         }
-    }
-    if (a.publish && K > 0) {
-        __syncthreads();
-        if (threadIdx.x == 0) st_release_gpu(a.chain_flags + tile_of(K - 1), a.chain_seq);
+        mbar_arrive(&done[st]); // this thread has read the stage and issued its stores for tile k
     }
 }
 
@@ -657,7 +674,7 @@ cudaError_t dispatch_tma(const typename E::P &p, const BatchArgs &a_in, const La
     cudaLaunchConfig_t cfg = {};
     const uint64_t slots = (uint64_t)stream_grid_slots();
     cfg.gridDim = dim3((unsigned)(tiles < slots ? tiles : slots));
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(STREAM_THREADS);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
