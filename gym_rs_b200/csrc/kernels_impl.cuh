@@ -247,6 +247,24 @@ step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Bat
     const int nvalid = live ? (full ? V : (int)(a.n - i0)) : 0;
     const A *actp = reinterpret_cast<const A *>(a.actions) + i0;
 
+    // Before any dependency is resolved: pull this CTA's input rows into L2 with one bulk prefetch
+    // per row (cp.async.bulk.prefetch.L2).  Always safe -- L2 is the point of coherence, so a line
+    // the previous launch is still writing is simply updated in place -- and it lets the HBM reads
+    // of launch t + 1 overlap the tail of launch t even when the launch has to wait for the whole
+    // previous grid (pdl = 1): after the wait the row loads are L2 hits.
+    if (a.l2_prefetch && threadIdx.x <= E::SD) {
+        const uint64_t cta0 = (uint64_t)blockIdx.x * blockDim.x * V;
+        if (cta0 < a.n) {
+            const uint64_t left = a.n - cta0, span = (uint64_t)blockDim.x * V;
+            const uint32_t bytes = (uint32_t)((left < span ? left : span) * 4u) & ~15u;
+            const void *src = threadIdx.x < E::SD
+                                  ? static_cast<const void *>(a.state + threadIdx.x * a.ld + cta0)
+                                  : static_cast<const void *>(reinterpret_cast<const A *>(a.actions) + cta0);
+            if (bytes && (reinterpret_cast<uintptr_t>(src) & 15u) == 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+        }
+    }
+
     A act[V];
     // pdl == 2: the caller guarantees the action batch predates the previous launch, so it can
     // be fetched before any dependency is resolved
@@ -612,7 +630,7 @@ cudaError_t launch_ex(K kernel, uint64_t threads, int block, bool pdl, cudaStrea
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (!pdl) { a.early_actions = 0; a.chain = 0; }
+    if (!pdl) { a.early_actions = 0; a.chain = 0; a.l2_prefetch = 0; }
     return cudaLaunchKernelEx(&cfg, kernel, p, a);
 }
 
@@ -624,6 +642,7 @@ cudaError_t dispatch_flags(const typename E::P &p, const BatchArgs &a_in, const 
     const bool sbt = E::HAS_SBT && o.use_sbt;
     BatchArgs a = a_in;
     a.early_actions = (o.pdl == 2);
+    a.l2_prefetch = use_l2_prefetch(o);
     const int key = (o.autoreset ? 4 : 0) | (sbt ? 2 : 0) | (o.time_limit ? 1 : 0);
 #define GYMRS_CASE(K, AR, SB, TL)                                                                   \
     case K:                                                                                         \
