@@ -358,8 +358,8 @@ int alloc_env(gymrs_env *e)
     const size_t chain_words = (size_t)((n + 31) / 32) + 2; // V = 1, 32-thread CTAs is the finest geometry
     CU(cudaMalloc(&e->chain_mem, chain_words * sizeof(uint32_t)));
     CU(cudaMemsetAsync(e->chain_mem, 0, chain_words * sizeof(uint32_t), e->stream));
-    CU(cudaHostAlloc(&e->err_host, 4 * sizeof(uint32_t), cudaHostAllocMapped));
-    std::memset(e->err_host, 0, 4 * sizeof(uint32_t));
+    CU(cudaHostAlloc(&e->err_host, 8 * sizeof(uint32_t), cudaHostAllocMapped));
+    std::memset(e->err_host, 0, 8 * sizeof(uint32_t));
     CU(cudaHostGetDevicePointer(&e->err_dev, e->err_host, 0));
     return GYMRS_OK;
 }
@@ -881,10 +881,12 @@ int gymrs_sync(gymrs_env *e, uint64_t *bad_env)
         const uint64_t gid = (uint64_t)e->err_host[1] | ((uint64_t)e->err_host[2] << 32);
         if (bad_env) *bad_env = gid;
         e->err_host[0] = 0;
-        char buf[96];
+        char buf[128];
         // the reference's panic text: "{} usize invalid" (cartpole.rs:404) /
-        // "{} (usize) invalid" (mountain_car.rs:404); the action value itself stays on the device
-        std::snprintf(buf, sizeof buf, "invalid action for env %llu", (unsigned long long)gid);
+        // "{} (usize) invalid" (mountain_car.rs:404), followed by where it happened
+        const int act = (int)e->err_host[4];
+        std::snprintf(buf, sizeof buf, e->kind == GYMRS_MOUNTAIN_CAR ? "%d (usize) invalid (env %llu)" : "%d usize invalid (env %llu)",
+                      act, (unsigned long long)gid);
         return fail(GYMRS_ERR_INVALID_ACTION, buf);
     }
     return GYMRS_OK;

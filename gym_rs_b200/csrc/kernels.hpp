@@ -27,7 +27,7 @@ struct BatchArgs {
     PhiloxKeys rk;       // Philox round keys of the handle's seed (philox_round_keys)
     uint64_t epoch;      // Philox counter high half for auto-resets in this step (rollout: first step)
     uint32_t *err;       // device-visible words: [0] invalid-action flag, [1..2] one offending global id,
-                         // [3] chained-dependency timeout flag
+                         // [3] chained-dependency timeout flag, [4] the offending action's bits
     int early_actions;   // step: read the action row before any dependency is resolved (LaunchOpts::pdl == 2)
     // chained launches: per-CTA progress flags of this handle (see kernels_impl.cuh)
     uint32_t *chain_flags; // [number of CTAs]; CTA b stores chain_seq here when its stores are done

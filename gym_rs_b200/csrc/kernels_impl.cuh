@@ -121,11 +121,12 @@ __device__ __forceinline__ void st_row(T *p, const T (&r)[V], int nvalid)
     }
 }
 
-__device__ __forceinline__ void report_invalid(uint32_t *err, uint64_t gid)
+__device__ __forceinline__ void report_invalid(uint32_t *err, uint64_t gid, uint32_t action_bits)
 {
     // sticky; any one offender is reported (the reference panics on the first it meets)
     err[1] = (uint32_t)gid;
     err[2] = (uint32_t)(gid >> 32);
+    err[4] = action_bits;
     __threadfence_system();
     *reinterpret_cast<volatile uint32_t *>(err) = 1u;
 }
@@ -165,7 +166,7 @@ __device__ __forceinline__ void transition(const typename E::P &p, const BatchAr
             }
             if (AR && (done || trunc)) need_reset |= 1u << j;
         } else if (j < nvalid) {
-            report_invalid(a.err, gid0 + j); //                            cartpole.rs:402-406
+            report_invalid(a.err, gid0 + j, (uint32_t)act[j]); //          cartpole.rs:402-406
         }
 #pragma unroll
         for (int r = 0; r < E::SD; ++r) s[r][j] = sj[r];
