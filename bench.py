@@ -123,6 +123,25 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run this rank (and allocate its pinned host buffers) on the CPUs NVML
+    reports as local to the GPU, so the e2e leg's host traffic does not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -218,6 +237,7 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
@@ -374,6 +394,7 @@ def run_b200(args):
                "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": D2H_BYTES[env] * n,
                "steps": args.e2e_steps,
                "pcie_gbs": (4 + D2H_BYTES[env]) * n * args.e2e_steps / dt / 1e9,
+               "host_cpus_bound_to_gpu_numa_node": numa,
                "synchronous_value": world * n / dt_sync,
                "api": "gymrs_step_host_async + gymrs_host_wait, two pinned buffer sets (actions in; obs, reward, "
                       "done out, every step); synchronous_value = gymrs_step_host, one step at a time"}
