@@ -836,6 +836,91 @@ def test_time_limit_truncation(torch, g):
     env.close()
 
 
+def test_pendulum_host_step_rollout_and_time_limit(torch, g):
+    """Continuous-action env through every entry point: host step (float actions), fused rollout with
+    TIME_LIMIT truncation + auto-reset, and theta staying wrapped over a long spin."""
+    n = 300001
+    r = np.random.default_rng(4)
+    env = g.PendulumEnv(num_envs=n, time_limit=True)
+    p = env.params
+    p.max_episode_steps = 9
+    env.params = p
+    env.reset(seed=6)
+    st0 = env.get_state()
+    act = r.uniform(-2.5, 2.5, n).astype(np.float32)
+    obs = np.empty((3, n), dtype=np.float32)
+    rew = np.empty(n, dtype=np.float32)
+    done = np.empty(n, dtype=np.uint8)
+    trunc = np.empty(n, dtype=np.uint8)
+    env.step_host(act, obs, rew, done, trunc, autoreset=True)
+    ref = oracle.step_batch(oracle.PENDULUM, st0, act)
+    assert_within(obs, ref["obs"], "pendulum host step obs")
+    assert_within(rew, ref["reward"], "pendulum host step reward")
+    assert not done.any() and not trunc.any()
+    # 20 fused steps with a horizon of 9: truncation at elapsed == 9 and 18 (1 host step + k rollout steps)
+    k = 20
+    acts = torch.as_tensor(r.uniform(-2, 2, (k, n)).astype(np.float32)).cuda()
+    done_out = torch.zeros((k, n), device="cuda", dtype=torch.uint8)
+    obs_out = torch.zeros((k, 3, n), device="cuda")
+    env.rollout(acts, obs_out, None, done_out, autoreset=True)
+    env.sync()
+    assert not done_out.any()                       # Pendulum never terminates
+    el = core_elapsed(env)
+    assert (el == (1 + k) % 9).all()                # 21 steps, reset at 9 and 18 -> 3 steps into the third episode
+    o = obs_out[-1].cpu().numpy()
+    assert np.abs(o[0] ** 2 + o[1] ** 2 - 1).max() < 1e-5 and np.abs(o[2]).max() <= 8.0
+    # constant maximal torque spins the pendulum up; the stored angle must stay wrapped
+    spin = g.PendulumEnv(num_envs=4096)
+    spin.reset(seed=1)
+    full = torch.full((4096,), 2.0, device="cuda")
+    for _ in range(600):
+        spin.step(full)
+    spin.sync()
+    th = spin.get_state()[0]
+    assert np.abs(th).max() <= math.pi + 1e-5 and np.isfinite(th).all()
+    env.close()
+    spin.close()
+
+
+def core_elapsed(env):
+    """device view of the TIME_LIMIT step counters (gymrs_buffers.elapsed_steps)"""
+    from gym_rs_b200.core import _as_tensor
+    return _as_tensor(env._buf.elapsed_steps, (env.num_envs,), "<i4", None, env.device).to("cpu").numpy().astype(np.int64)
+
+
+def test_clone_and_stream_switch_keep_chained_state_consistent(torch, g):
+    """Clone after chained (pdl = 2) steps, then keep stepping both; switch the original to another
+    stream in the middle.  Both must track a plainly-launched reference handle bit for bit."""
+    n = 1 << 18
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    acts = [torch.randint(0, 2, (n,), generator=gen, device="cuda", dtype=torch.int32) for _ in range(6)]
+    torch.cuda.synchronize()
+    a = g.CartPoleEnv(num_envs=n)
+    ref = g.CartPoleEnv(num_envs=n)
+    a.set_launch_config(pdl=2)
+    ref.set_launch_config(pdl=0)
+    for e in (a, ref):
+        e.reset(seed=17)
+    for t in range(30):
+        a.step(acts[t % 6], autoreset=True)
+        ref.step(acts[t % 6], autoreset=True)
+    twin = a.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    a.set_stream(side.cuda_stream)
+    for t in range(30, 60):
+        with torch.cuda.stream(side):
+            a.step(acts[t % 6], autoreset=True)
+        twin.step(acts[t % 6], autoreset=True)
+        ref.step(acts[t % 6], autoreset=True)
+    for e in (a, twin, ref):
+        e.sync()
+    s = ref.get_state()
+    assert np.array_equal(a.get_state(), s) and np.array_equal(twin.get_state(), s)
+    for e in (a, twin, ref):
+        e.close()
+
+
 def test_clone_is_a_deep_copy(torch, g):
     n = 10000
     env = g.CartPoleEnv(num_envs=n)
