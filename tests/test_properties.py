@@ -12,7 +12,7 @@ import oracle
 finite = st.floats(allow_nan=False, allow_infinity=False, width=64, min_value=-1e6, max_value=1e6)
 
 
-@settings(max_examples=300, deadline=None)
+@settings(max_examples=300, deadline=None, derandomize=True)
 @given(v=st.floats(allow_nan=True, allow_infinity=True), lo=finite, width=st.floats(min_value=0, max_value=1e6))
 def test_clip_properties(v, lo, width):
     """util_fns.rs:2-10 on OrderedFloat: result in [lo, hi]; identity inside; idempotent; NaN -> hi."""
@@ -27,13 +27,13 @@ def test_clip_properties(v, lo, width):
     assert L.orc_clip(r, lo, hi) == r
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True)
 @given(n=st.integers(min_value=0, max_value=2 ** 40), v=st.integers(min_value=0, max_value=2 ** 41))
 def test_discrete_contains_is_less_than(n, v):
     assert bool(oracle.lib().orc_discrete_contains(n, v)) == (v < n)   # discrete.rs:14-20
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True)
 @given(x=st.floats(-3, 3), xd=st.floats(-5, 5), th=st.floats(-0.5, 0.5), thd=st.floats(-5, 5), a=st.integers(0, 1))
 def test_cartpole_mirror_symmetry(x, xd, th, thd, a):
     """The dynamics are odd under (state, force) -> (-state, -force): every IEEE operation involved
@@ -45,7 +45,7 @@ def test_cartpole_mirror_symmetry(x, xd, th, thd, a):
     assert r1["done"][0] == r2["done"][0] and r1["reward"][0] == r2["reward"][0]
 
 
-@settings(max_examples=300, deadline=None)
+@settings(max_examples=300, deadline=None, derandomize=True)
 @given(p=st.floats(-2, 1), v=st.floats(-0.2, 0.2), a=st.integers(0, 2))
 def test_mountain_car_stays_in_its_box(p, v, a):
     """After the two clips (mountain_car.rs:413-416) the state is inside the observation space, the
@@ -59,7 +59,7 @@ def test_mountain_car_stays_in_its_box(p, v, a):
     assert r["reward"][0] == -1.0
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True)
 @given(th=st.floats(-20, 20), thd=st.floats(-8, 8), u=st.floats(-5, 5))
 def test_pendulum_invariants(th, thd, u):
     r = oracle.step_batch(oracle.PENDULUM, np.array([[th], [thd]]), [u])
@@ -75,7 +75,7 @@ def test_pendulum_invariants(th, thd, u):
     assert np.abs(r3["obs"] - r["obs"]).max() < 1e-9
 
 
-@settings(max_examples=100, deadline=None)
+@settings(max_examples=100, deadline=None, derandomize=True)
 @given(seed=st.integers(0, 2 ** 64 - 1), gid=st.integers(0, 2 ** 40), epoch=st.integers(0, 2 ** 32))
 def test_reset_is_a_pure_function_of_seed_id_epoch(seed, gid, epoch):
     a = oracle.reset_batch(oracle.CARTPOLE, 1, seed=seed, global_env_offset=gid, epoch=epoch)
