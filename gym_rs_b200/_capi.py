@@ -44,6 +44,12 @@ class Buffers(C.Structure):
                 ("steps_beyond_terminated", C.c_void_p), ("elapsed_steps", C.c_void_p)]
 
 
+class CheckpointInfo(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("flags", C.c_uint32), ("num_envs", C.c_uint64),
+                ("global_env_offset", C.c_uint64), ("seed", C.c_uint64), ("step_count", C.c_uint64),
+                ("bytes", C.c_uint64)]
+
+
 _vp, _u64, _u32, _i = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
 _pu64 = C.POINTER(C.c_uint64)
 
@@ -69,6 +75,11 @@ SIGNATURES = {
     "gymrs_get_state": (_i, [_vp, _vp, _vp]),
     "gymrs_set_state": (_i, [_vp, _vp, _vp]),
     "gymrs_get_buffers": (_i, [_vp, C.POINTER(Buffers)]),
+    "gymrs_checkpoint_size": (_i, [_vp, C.POINTER(C.c_size_t)]),
+    "gymrs_checkpoint_save": (_i, [_vp, _vp, C.c_size_t]),
+    "gymrs_checkpoint_load": (_i, [_vp, _vp, C.c_size_t]),
+    "gymrs_checkpoint_create": (_i, [_vp, C.c_size_t, _i, C.POINTER(_vp)]),
+    "gymrs_checkpoint_info_of": (_i, [_vp, C.c_size_t, C.POINTER(CheckpointInfo)]),
     "gymrs_action_space": (_i, [_vp, _pu64, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gymrs_observation_space": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gymrs_reward_range": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -356,11 +356,64 @@ class Env(EnvProperties):
                 "params": {k: getattr(p, k) for k, _ in p._fields_ if not k.startswith("_")},
                 "state": st.tolist(), "steps_beyond_terminated": None if sbt is None else sbt.tolist()}
 
+    # ---- checkpoint / resume (exact: carries the reset stream's key and step counter) ------
+    def checkpoint(self):
+        """gymrs_checkpoint_save: the whole handle as one numpy uint8 blob.  Unlike serialize()
+        (which skips the RNG like the reference's serde derive), a handle restored from the blob
+        continues bit-identically, auto-resets included."""
+        import numpy as np
+        nbytes = C.c_size_t()
+        _capi.check(self._L.gymrs_checkpoint_size(self._h, C.byref(nbytes)))
+        buf = np.empty(nbytes.value, dtype=np.uint8)
+        _capi.check(self._L.gymrs_checkpoint_save(self._h, buf.ctypes.data_as(C.c_void_p), buf.nbytes))
+        return buf
+
+    def restore(self, blob):
+        """gymrs_checkpoint_load into this handle (same kind, num_envs and time_limit)."""
+        import numpy as np
+        buf = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8))
+        _capi.check(self._L.gymrs_checkpoint_load(self._h, buf.ctypes.data_as(C.c_void_p), buf.nbytes))
+        self._refresh_spaces()
+        self._seed_used = checkpoint_info(buf)["seed"]
+
+    @classmethod
+    def from_checkpoint(cls, blob, device: int = 0):
+        """gymrs_checkpoint_create: a new handle on `device` built from the blob alone."""
+        import numpy as np
+        import torch
+        buf = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8))
+        info = checkpoint_info(buf)
+        if info["kind"] != cls.KIND:
+            raise ValueError(f"checkpoint holds env kind {info['kind']}, not {cls.KIND}")
+        self = object.__new__(cls)
+        self._L = _capi.load()
+        self._h = C.c_void_p()
+        self.num_envs = info["num_envs"]
+        self.device = int(device)
+        self._metadata = cls._METADATA
+        self._seed_used = info["seed"]
+        _capi.check(self._L.gymrs_checkpoint_create(buf.ctypes.data_as(C.c_void_p), buf.nbytes, self.device,
+                                                    C.byref(self._h)))
+        self._refresh_views()
+        self._refresh_spaces()
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        return self
+
     def __del__(self):
         try:
             self.close()
         except Exception:
             pass
+
+
+def checkpoint_info(blob) -> dict:
+    """gymrs_checkpoint_info_of: validates a blob (magic, version, size, checksum) on the host and
+    returns its header fields; raises GymrsError for anything that is not an intact checkpoint."""
+    import numpy as np
+    buf = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8))
+    info = _capi.CheckpointInfo()
+    _capi.check(_capi.load().gymrs_checkpoint_info_of(buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(info)))
+    return {k: int(getattr(info, k)) for k, _ in info._fields_}
 
 
 def _obs_values(o):

@@ -793,6 +793,212 @@ int gymrs_set_state(gymrs_env *e, const float *state, const int32_t *sbt)
     return GYMRS_OK;
 }
 
+// ---- checkpoint / resume ----------------------------------------------------------------
+// Blob = CkptHeader (256 bytes) + the handle's per-env arrays packed densely ([rows][num_envs],
+// no row padding), each section rounded up to 8 bytes.  The checksum covers header + payload.
+} // extern "C"
+
+namespace {
+
+struct CkptHeader {
+    char magic[8];
+    uint32_t version, kind;
+    uint64_t n, global_off;
+    uint32_t flags, sbt_dirty;
+    uint64_t seed, step_count;
+    uint64_t total_bytes;
+    uint64_t checksum; // of the whole blob with this field zero
+    float reset_low[4], reset_high[4];
+    unsigned char params[96]; // gymrs_<kind>_params, zero padded
+    unsigned char reserved[56];
+};
+static_assert(sizeof(CkptHeader) == 256, "checkpoint header is 256 bytes");
+static_assert(sizeof(gymrs_cartpole_params) <= 96 && sizeof(gymrs_mountain_car_params) <= 96 &&
+              sizeof(gymrs_pendulum_params) <= 96, "params fit the header");
+const char CKPT_MAGIC[8] = {'G', 'Y', 'M', 'R', 'S', 'C', 'K', 'P'};
+constexpr uint32_t CKPT_VERSION = 1;
+
+size_t pad8(size_t b) { return (b + 7) & ~(size_t)7; }
+
+struct CkptLayout {
+    size_t state, obs, reward, done, truncated, sbt, elapsed, total; // byte offsets; 0 = absent
+};
+
+CkptLayout ckpt_layout(int kind, uint64_t n, uint32_t flags)
+{
+    const uint32_t sd = kind == GYMRS_CARTPOLE ? 4 : 2;
+    CkptLayout l = {};
+    size_t off = sizeof(CkptHeader);
+    l.state = off; off += pad8(sizeof(float) * sd * n);
+    if (kind == GYMRS_PENDULUM) { l.obs = off; off += pad8(sizeof(float) * 3 * n); }
+    l.reward = off; off += pad8(sizeof(float) * n);
+    l.done = off; off += pad8(n);
+    l.truncated = off; off += pad8(n);
+    if (kind == GYMRS_CARTPOLE) { l.sbt = off; off += pad8(sizeof(int32_t) * n); }
+    if (flags & GYMRS_FLAG_TIME_LIMIT) { l.elapsed = off; off += pad8(sizeof(uint32_t) * n); }
+    l.total = off;
+    return l;
+}
+
+// 64-bit multiply-xorshift hash over 8-byte words (every section is padded to 8 bytes)
+uint64_t ckpt_hash(const unsigned char *p, size_t bytes, size_t skip_off)
+{
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)bytes;
+    for (size_t i = 0; i + 8 <= bytes; i += 8) {
+        uint64_t w;
+        std::memcpy(&w, p + i, 8);
+        if (i == skip_off) w = 0;
+        h = (h ^ w) * 0xFF51AFD7ED558CCDull;
+        h ^= h >> 29;
+    }
+    return h;
+}
+
+int ckpt_parse(const void *buf, size_t bytes, CkptHeader *h)
+{
+    if (!buf) return fail(GYMRS_ERR_BAD_ARG, "checkpoint buffer is NULL");
+    if (bytes < sizeof(CkptHeader)) return fail(GYMRS_ERR_BAD_ARG, "checkpoint blob shorter than its header");
+    std::memcpy(h, buf, sizeof *h);
+    if (std::memcmp(h->magic, CKPT_MAGIC, 8) != 0) return fail(GYMRS_ERR_BAD_ARG, "not a gymrs checkpoint (bad magic)");
+    if (h->version != CKPT_VERSION) return fail(GYMRS_ERR_UNSUPPORTED, "unsupported checkpoint version");
+    if (h->kind > (uint32_t)GYMRS_PENDULUM || h->n == 0 || h->n > (1ull << 40))
+        return fail(GYMRS_ERR_BAD_ARG, "corrupt checkpoint header");
+    const CkptLayout l = ckpt_layout((int)h->kind, h->n, h->flags);
+    if (h->total_bytes != l.total || bytes < l.total) return fail(GYMRS_ERR_BAD_ARG, "checkpoint blob is truncated");
+    if (ckpt_hash((const unsigned char *)buf, l.total, offsetof(CkptHeader, checksum)) != h->checksum)
+        return fail(GYMRS_ERR_BAD_ARG, "checkpoint checksum mismatch");
+    return GYMRS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int gymrs_checkpoint_size(const gymrs_env *e, size_t *bytes)
+{
+    if (!e || !bytes) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    *bytes = ckpt_layout(e->kind, e->n, e->flags).total;
+    return GYMRS_OK;
+}
+
+int gymrs_checkpoint_info_of(const void *buf, size_t bytes, gymrs_checkpoint_info *info)
+{
+    if (!info) return fail(GYMRS_ERR_BAD_ARG, "info is NULL");
+    CkptHeader h;
+    if (int rc = ckpt_parse(buf, bytes, &h)) return rc;
+    info->kind = (int32_t)h.kind;
+    info->flags = h.flags;
+    info->num_envs = h.n;
+    info->global_env_offset = h.global_off;
+    info->seed = h.seed;
+    info->step_count = h.step_count;
+    info->bytes = h.total_bytes;
+    return GYMRS_OK;
+}
+
+int gymrs_checkpoint_save(gymrs_env *e, void *buf, size_t bytes)
+{
+    if (!e || !buf) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    const CkptLayout l = ckpt_layout(e->kind, e->n, e->flags);
+    if (bytes < l.total) return fail(GYMRS_ERR_BAD_ARG, "checkpoint buffer too small (see gymrs_checkpoint_size)");
+    ON_DEVICE(e->device);
+    if (int rc_ = drain_host(e)) return rc_;
+    unsigned char *out = (unsigned char *)buf;
+    std::memset(out, 0, l.total); // section padding is part of the checksum
+    const uint64_t n = e->n;
+    cudaStream_t s = e->stream;
+    CU(cudaMemcpy2DAsync(out + l.state, sizeof(float) * n, e->state, sizeof(float) * e->ld, sizeof(float) * n,
+                         e->state_dim, cudaMemcpyDeviceToHost, s));
+    if (l.obs)
+        CU(cudaMemcpy2DAsync(out + l.obs, sizeof(float) * n, e->obs, sizeof(float) * e->ld, sizeof(float) * n,
+                             e->obs_dim, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(out + l.reward, e->reward, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(out + l.done, e->done, n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(out + l.truncated, e->truncated, n, cudaMemcpyDeviceToHost, s));
+    if (l.sbt) CU(cudaMemcpyAsync(out + l.sbt, e->sbt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    if (l.elapsed) CU(cudaMemcpyAsync(out + l.elapsed, e->elapsed, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
+    CkptHeader h = {};
+    std::memcpy(h.magic, CKPT_MAGIC, 8);
+    h.version = CKPT_VERSION;
+    h.kind = (uint32_t)e->kind;
+    h.n = n;
+    h.global_off = e->global_off;
+    h.flags = e->flags;
+    h.sbt_dirty = e->sbt_dirty ? 1u : 0u;
+    h.seed = e->seed;
+    h.step_count = e->step_count;
+    h.total_bytes = l.total;
+    std::memcpy(h.reset_low, e->reset_low, sizeof h.reset_low);
+    std::memcpy(h.reset_high, e->reset_high, sizeof h.reset_high);
+    if (e->kind == GYMRS_CARTPOLE) std::memcpy(h.params, &e->cp, sizeof e->cp);
+    else if (e->kind == GYMRS_MOUNTAIN_CAR) std::memcpy(h.params, &e->mc, sizeof e->mc);
+    else std::memcpy(h.params, &e->pd, sizeof e->pd);
+    CU(cudaStreamSynchronize(s));
+    std::memcpy(out, &h, sizeof h);
+    h.checksum = ckpt_hash(out, l.total, offsetof(CkptHeader, checksum));
+    std::memcpy(out, &h, sizeof h);
+    return GYMRS_OK;
+}
+
+int gymrs_checkpoint_load(gymrs_env *e, const void *buf, size_t bytes)
+{
+    if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
+    CkptHeader h;
+    if (int rc = ckpt_parse(buf, bytes, &h)) return rc;
+    if ((int)h.kind != e->kind) return fail(GYMRS_ERR_BAD_ARG, "checkpoint is of a different env kind");
+    if (h.n != e->n) return fail(GYMRS_ERR_BAD_ARG, "checkpoint holds a different number of envs");
+    if ((h.flags ^ e->flags) & GYMRS_FLAG_TIME_LIMIT)
+        return fail(GYMRS_ERR_BAD_ARG, "checkpoint and handle differ in GYMRS_FLAG_TIME_LIMIT");
+    ON_DEVICE(e->device);
+    if (int rc_ = drain_host(e)) return rc_;
+    const CkptLayout l = ckpt_layout(e->kind, e->n, e->flags);
+    const unsigned char *in = (const unsigned char *)buf;
+    const uint64_t n = e->n;
+    cudaStream_t s = e->stream;
+    e->chain_ok = false;
+    CU(cudaMemcpy2DAsync(e->state, sizeof(float) * e->ld, in + l.state, sizeof(float) * n, sizeof(float) * n,
+                         e->state_dim, cudaMemcpyHostToDevice, s));
+    if (l.obs)
+        CU(cudaMemcpy2DAsync(e->obs, sizeof(float) * e->ld, in + l.obs, sizeof(float) * n, sizeof(float) * n,
+                             e->obs_dim, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->reward, in + l.reward, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->done, in + l.done, n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->truncated, in + l.truncated, n, cudaMemcpyHostToDevice, s));
+    if (l.sbt) CU(cudaMemcpyAsync(e->sbt, in + l.sbt, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    if (l.elapsed) CU(cudaMemcpyAsync(e->elapsed, in + l.elapsed, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+    e->global_off = h.global_off;
+    e->seed = h.seed;
+    e->step_count = h.step_count;
+    e->sbt_dirty = h.sbt_dirty != 0;
+    std::memcpy(e->reset_low, h.reset_low, sizeof h.reset_low);
+    std::memcpy(e->reset_high, h.reset_high, sizeof h.reset_high);
+    if (e->kind == GYMRS_CARTPOLE) std::memcpy(&e->cp, h.params, sizeof e->cp);
+    else if (e->kind == GYMRS_MOUNTAIN_CAR) std::memcpy(&e->mc, h.params, sizeof e->mc);
+    else std::memcpy(&e->pd, h.params, sizeof e->pd);
+    fold_params(e);
+    return GYMRS_OK;
+}
+
+int gymrs_checkpoint_create(const void *buf, size_t bytes, int device, gymrs_env **out)
+{
+    if (!out) return fail(GYMRS_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    CkptHeader h;
+    if (int rc = ckpt_parse(buf, bytes, &h)) return rc;
+    gymrs_env *e = nullptr;
+    int rc = gymrs_create((int)h.kind, h.n, device, h.global_off, h.params, h.flags & GYMRS_FLAG_TIME_LIMIT, &e);
+    if (rc != GYMRS_OK) return rc;
+    rc = gymrs_checkpoint_load(e, buf, bytes);
+    if (rc != GYMRS_OK) {
+        std::string msg = g_last_error;
+        free_env(e);
+        return fail(rc, msg);
+    }
+    *out = e;
+    return GYMRS_OK;
+}
+
 int gymrs_get_buffers(gymrs_env *e, gymrs_buffers *out)
 {
     if (!e || !out) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");

@@ -141,6 +141,22 @@ template <class Derived, class Obs, int KIND, int DIM> class EnvBase {
         handle_ = nullptr;
     }
 
+    // `Env: Serialize` (core.rs:25): the handle as one blob, reset stream included, so restore()
+    // resumes bit-identically (the reference's serde derive skips its RNG, cartpole.rs:85-86)
+    std::vector<unsigned char> checkpoint()
+    {
+        size_t bytes = 0;
+        check(gymrs_checkpoint_size(handle_, &bytes));
+        std::vector<unsigned char> blob(bytes);
+        check(gymrs_checkpoint_save(handle_, blob.data(), bytes));
+        return blob;
+    }
+    void restore(const std::vector<unsigned char> &blob)
+    {
+        check(gymrs_checkpoint_load(handle_, blob.data(), blob.size()));
+        pull_state();
+    }
+
     // EnvProperties, core.rs:60-90
     RewardRange reward_range() const { return {}; }
     uint64_t rand_random() const { return seed_used_; }

@@ -177,6 +177,33 @@ int gymrs_get_state(gymrs_env *env, float *state, int32_t *sbt);
 int gymrs_set_state(gymrs_env *env, const float *state, const int32_t *sbt);
 int gymrs_get_buffers(gymrs_env *env, gymrs_buffers *out);
 
+/* ---- checkpoint / resume: `Env: Clone + Serialize` (core.rs:25; derive(Serialize)
+ *      cartpole.rs:51, mountain_car.rs:46-47) ----
+ * A checkpoint is one self-describing host blob: a 256-byte header (kind, num_envs, flags,
+ * global offset, the `pub` physics fields, reset bounds) followed by every per-env array of the
+ * handle (state, observation, reward, done, truncated, steps_beyond_terminated, elapsed steps).
+ * The reference skips its RNG when serialising (serde(skip_serializing), cartpole.rs:85-86,
+ * mountain_car.rs:79-81) because a PCG64 state cannot be rebuilt from plain data; here reset
+ * sampling is counter-based, so the blob also carries the Philox key and the step counter and a
+ * restored handle continues BIT-IDENTICALLY to the one that was saved, auto-resets included.
+ * save / load / create synchronise.  load needs a handle of the same kind, num_envs and
+ * TIME_LIMIT flag; create builds a new handle on `device` from the blob alone. */
+typedef struct gymrs_checkpoint_info {
+    int32_t kind;
+    uint32_t flags;
+    uint64_t num_envs;
+    uint64_t global_env_offset;
+    uint64_t seed;       /* Philox key of the reset stream */
+    uint64_t step_count; /* steps since the last full reset */
+    uint64_t bytes;      /* total size of the blob */
+} gymrs_checkpoint_info;
+int gymrs_checkpoint_size(const gymrs_env *env, size_t *bytes);
+int gymrs_checkpoint_save(gymrs_env *env, void *buf, size_t bytes);
+int gymrs_checkpoint_load(gymrs_env *env, const void *buf, size_t bytes);
+int gymrs_checkpoint_create(const void *buf, size_t bytes, int device, gymrs_env **out);
+/* Validates magic, version, size and checksum of a blob without touching a device. */
+int gymrs_checkpoint_info_of(const void *buf, size_t bytes, gymrs_checkpoint_info *info);
+
 /* ---- EnvProperties (core.rs:60-90) ---- */
 /* Discrete(n): *n = 2 / 3, low/high untouched.  Box (Pendulum): *n = 0, low/high = -+max_torque. */
 int gymrs_action_space(const gymrs_env *env, uint64_t *n, float *low, float *high);

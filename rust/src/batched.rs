@@ -85,6 +85,22 @@ impl BatchedEnv {
         BatchStep { observation: &self.obs, reward: &self.reward, done: &self.done, truncated: &self.truncated }
     }
 
+    /// The whole handle as one blob (`Env: Serialize`, core.rs:25).  Unlike the reference's serde
+    /// derive, which skips the RNG (cartpole.rs:85-86), the blob carries the counter-based reset
+    /// stream, so [`BatchedEnv::restore`] resumes bit-identically.
+    pub fn checkpoint(&mut self) -> Vec<u8> {
+        let mut bytes = 0usize;
+        unsafe { ffi::check(ffi::gymrs_checkpoint_size(self.handle, &mut bytes)) };
+        let mut blob = vec![0u8; bytes];
+        unsafe { ffi::check(ffi::gymrs_checkpoint_save(self.handle, blob.as_mut_ptr() as *mut c_void, bytes)) };
+        blob
+    }
+
+    /// Loads a blob written by a handle of the same kind, size and time-limit flag.
+    pub fn restore(&mut self, blob: &[u8]) {
+        unsafe { ffi::check(ffi::gymrs_checkpoint_load(self.handle, blob.as_ptr() as *const c_void, blob.len())) };
+    }
+
     pub fn num_envs(&self) -> usize {
         self.num_envs
     }

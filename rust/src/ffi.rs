@@ -62,6 +62,18 @@ pub struct gymrs_buffers {
     pub elapsed_steps: *mut u32,
 }
 
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct gymrs_checkpoint_info {
+    pub kind: i32,
+    pub flags: u32,
+    pub num_envs: u64,
+    pub global_env_offset: u64,
+    pub seed: u64,
+    pub step_count: u64,
+    pub bytes: u64,
+}
+
 extern "C" {
     pub fn gymrs_abi_version() -> c_int;
     pub fn gymrs_last_error() -> *const c_char;
@@ -80,11 +92,19 @@ extern "C" {
     pub fn gymrs_step(env: *mut gymrs_env, actions: *const c_void, step_flags: u32) -> c_int;
     pub fn gymrs_step_host(env: *mut gymrs_env, actions: *const c_void, step_flags: u32, obs: *mut f32,
                            reward: *mut f32, done: *mut u8, truncated: *mut u8) -> c_int;
+    pub fn gymrs_step_host_async(env: *mut gymrs_env, actions: *const c_void, step_flags: u32, obs: *mut f32,
+                                 reward: *mut f32, done: *mut u8, truncated: *mut u8, ticket: *mut u64) -> c_int;
+    pub fn gymrs_host_wait(env: *mut gymrs_env, ticket: u64) -> c_int;
     pub fn gymrs_rollout(env: *mut gymrs_env, actions: *const c_void, n_steps: u32, step_flags: u32,
                          obs_out: *mut f32, reward_out: *mut f32, done_out: *mut u8) -> c_int;
     pub fn gymrs_get_state(env: *mut gymrs_env, state: *mut f32, sbt: *mut i32) -> c_int;
     pub fn gymrs_set_state(env: *mut gymrs_env, state: *const f32, sbt: *const i32) -> c_int;
     pub fn gymrs_get_buffers(env: *mut gymrs_env, out: *mut gymrs_buffers) -> c_int;
+    pub fn gymrs_checkpoint_size(env: *const gymrs_env, bytes: *mut usize) -> c_int;
+    pub fn gymrs_checkpoint_save(env: *mut gymrs_env, buf: *mut c_void, bytes: usize) -> c_int;
+    pub fn gymrs_checkpoint_load(env: *mut gymrs_env, buf: *const c_void, bytes: usize) -> c_int;
+    pub fn gymrs_checkpoint_create(buf: *const c_void, bytes: usize, device: c_int, out: *mut *mut gymrs_env) -> c_int;
+    pub fn gymrs_checkpoint_info_of(buf: *const c_void, bytes: usize, info: *mut gymrs_checkpoint_info) -> c_int;
     pub fn gymrs_action_space(env: *const gymrs_env, n: *mut u64, low: *mut f32, high: *mut f32) -> c_int;
     pub fn gymrs_observation_space(env: *const gymrs_env, low: *mut f64, high: *mut f64) -> c_int;
     pub fn gymrs_reward_range(env: *const gymrs_env, low: *mut f64, high: *mut f64) -> c_int;

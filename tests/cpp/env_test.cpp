@@ -87,6 +87,16 @@ static void cartpole_plumbing()
     CartPoleEnv twin(env);
     auto a = env.step(0), b = twin.step(0);
     EXPECT(a.observation.to_vec() == b.observation.to_vec());
+    // Serialize: checkpoint, diverge, restore, and the restored env retraces the same steps
+    auto blob = env.checkpoint();
+    std::vector<double> first = env.step(1).observation.to_vec();
+    env.step(0);
+    env.restore(blob);
+    EXPECT(env.step(1).observation.to_vec() == first);
+    gymrs_checkpoint_info info;
+    EXPECT(gymrs_checkpoint_info_of(blob.data(), blob.size(), &info) == GYMRS_OK && info.kind == GYMRS_CARTPOLE && info.num_envs == 1);
+    blob[blob.size() / 2] ^= 1;
+    EXPECT(gymrs_checkpoint_info_of(blob.data(), blob.size(), &info) == GYMRS_ERR_BAD_ARG);
     // options: BoxR bounds for this reset only (cartpole.rs:351-365)
     spaces::BoxR<CartPoleObservation> box{{1, 2, 3, 4}, {2, 3, 4, 5}};
     auto st = env.reset(1, false, box).first;
