@@ -139,6 +139,12 @@ struct gymrs_env {
 
     uint64_t seed = 0;       // Philox key of the auto-reset stream
     uint64_t step_count = 0; // steps since the last full reset; epoch of an auto-reset = step_count + 1
+    // Device copy of step_count (+ a CTA arrival counter), see BatchArgs::epoch_dev.  Once a step of
+    // this handle has been captured into a CUDA graph the host can no longer count steps (replays
+    // happen behind its back): from then on the device copy is the authority (device_counted),
+    // kernels read and advance it themselves, and step_count is refreshed from it when needed.
+    uint64_t *epoch_mem = nullptr;
+    bool device_counted = false;
     bool sbt_dirty = false;  // some env may hold steps_beyond_terminated = Some(_)
     int vec = 0, block = 0, pdl = 1;
 };
@@ -220,6 +226,8 @@ BatchArgs base_args(const gymrs_env *e)
     a.global_off = e->global_off;
     a.rk = philox_round_keys(e->seed);
     a.epoch = e->step_count + 1;
+    a.epoch_dev = e->epoch_mem;
+    a.epoch_from_dev = e->device_counted ? 1 : 0;
     a.err = e->err_dev;
     a.chain_flags = e->chain_mem + 1;
     a.chain_seq = e->chain_seq;
@@ -295,6 +303,35 @@ int drain_host(gymrs_env *e)
     return GYMRS_OK;
 }
 
+// Is the handle's stream being captured into a CUDA graph?  (The legacy default stream cannot be.)
+bool capturing(const gymrs_env *e)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(e->stream, &st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return st == cudaStreamCaptureStatusActive;
+}
+
+// A step is about to be recorded into a graph: from now on the device counts this handle's steps.
+// Entry points that cannot be captured (they synchronise or use several streams) refuse instead.
+int refuse_in_capture(const gymrs_env *e, const char *what)
+{
+    if (!capturing(e)) return GYMRS_OK;
+    return fail(GYMRS_ERR_UNSUPPORTED, std::string(what) + " cannot be captured into a CUDA graph "
+                "(only gymrs_step, gymrs_rollout and a seeded full gymrs_reset can)");
+}
+
+// Bring the host's step_count up to date with the device copy (synchronises the stream).
+int refresh_step_count(gymrs_env *e)
+{
+    if (!e->device_counted) return GYMRS_OK;
+    CU(cudaMemcpyAsync(&e->step_count, e->epoch_mem, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return GYMRS_OK;
+}
+
 void after_step(gymrs_env *e, uint32_t step_flags, uint32_t n_steps)
 {
     e->step_count += n_steps;
@@ -316,6 +353,7 @@ int free_env(gymrs_env *e)
     cudaFree(e->elapsed);
     cudaFree(e->d_actions);
     cudaFree(e->chain_mem);
+    cudaFree(e->epoch_mem);
     if (e->err_host) cudaFreeHost(e->err_host);
     for (auto &s : e->copy_streams) if (s) cudaStreamDestroy(s);
     for (auto &v : e->hev) if (v) cudaEventDestroy(v);
@@ -358,6 +396,8 @@ int alloc_env(gymrs_env *e)
     const size_t chain_words = (size_t)((n + 31) / 32) + 2; // V = 1, 32-thread CTAs is the finest geometry
     CU(cudaMalloc(&e->chain_mem, chain_words * sizeof(uint32_t)));
     CU(cudaMemsetAsync(e->chain_mem, 0, chain_words * sizeof(uint32_t), e->stream));
+    CU(cudaMalloc(&e->epoch_mem, 4 * sizeof(uint64_t)));
+    CU(cudaMemsetAsync(e->epoch_mem, 0, 4 * sizeof(uint64_t), e->stream));
     CU(cudaHostAlloc(&e->err_host, 8 * sizeof(uint32_t), cudaHostAllocMapped));
     std::memset(e->err_host, 0, 8 * sizeof(uint32_t));
     CU(cudaHostGetDevicePointer(&e->err_dev, e->err_host, 0));
@@ -474,6 +514,7 @@ int gymrs_clone(const gymrs_env *src, gymrs_env **out)
 {
     if (!src || !out) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     *out = nullptr;
+    if (int rc_ = refuse_in_capture(src, "gymrs_clone")) return rc_;
     ON_DEVICE(src->device);
     gymrs_env *e = new (std::nothrow) gymrs_env();
     if (!e) return fail(GYMRS_ERR_ALLOC, "host allocation failed");
@@ -485,6 +526,7 @@ int gymrs_clone(const gymrs_env *src, gymrs_env **out)
     std::memcpy(e->reset_high, src->reset_high, sizeof e->reset_high);
     e->seed = src->seed; e->step_count = src->step_count; e->sbt_dirty = src->sbt_dirty;
     e->vec = src->vec; e->block = src->block; e->pdl = src->pdl;
+    e->device_counted = src->device_counted;
     int rc = alloc_env(e);
     if (rc != GYMRS_OK) {
         std::string msg = g_last_error;
@@ -504,6 +546,10 @@ int gymrs_clone(const gymrs_env *src, gymrs_env **out)
     cp(e->truncated, src->truncated, e->ld);
     cp(e->sbt, src->sbt, sizeof(int32_t) * e->ld);
     cp(e->elapsed, src->elapsed, sizeof(uint32_t) * e->ld);
+    cp(e->epoch_mem, src->epoch_mem, sizeof(uint64_t));         // the count, not the arrival counter
+    cp(e->epoch_mem + 2, src->epoch_mem + 2, sizeof(uint64_t)); // the seed
+    if (ce == cudaSuccess && src->device_counted)
+        ce = cudaMemcpyAsync(&e->step_count, e->epoch_mem, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     if (ce != cudaSuccess) {
         free_env(e);
@@ -535,6 +581,7 @@ int gymrs_get_params(const gymrs_env *e, void *params)
 int gymrs_set_stream(gymrs_env *e, void *cuda_stream)
 {
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
+    if (int rc_ = refuse_in_capture(e, "gymrs_set_stream")) return rc_;
     ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
     CU(cudaStreamSynchronize(e->stream));
@@ -566,6 +613,9 @@ int gymrs_reset(gymrs_env *e, const uint64_t *seed, const float *low, const floa
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
     if ((low == nullptr) != (high == nullptr)) return fail(GYMRS_ERR_BAD_ARG, "low and high must be given together");
     ON_DEVICE(e->device);
+    const bool cap = capturing(e);
+    if (cap && (!seed || mask)) return fail(GYMRS_ERR_UNSUPPORTED, "only a seeded full gymrs_reset can be captured into a CUDA graph");
+    if (cap && e->host_inflight) return fail(GYMRS_ERR_UNSUPPORTED, "a host step is in flight: gymrs_host_wait before capturing");
     if (int rc_ = drain_host(e)) return rc_;
     const uint64_t s = seed ? *seed : entropy64(); // seeding.rs:22
     if (seed_used) *seed_used = s;
@@ -593,7 +643,7 @@ int gymrs_reset(gymrs_env *e, const uint64_t *seed, const float *low, const floa
     fold_params(e);
     if (ce != cudaSuccess) return cuda_fail(ce, "reset launch");
     if (!mask) { // a full reset restarts the handle's auto-reset stream
-        e->seed = s;
+        e->seed = s; // the reset kernel also zeroes the device step counter and records the seed
         e->step_count = 0;
         e->sbt_dirty = false;
     }
@@ -604,10 +654,16 @@ int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
 {
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     ON_DEVICE(e->device);
+    if (capturing(e)) {
+        if (e->host_inflight) return fail(GYMRS_ERR_UNSUPPORTED, "a host step is in flight: gymrs_host_wait before capturing");
+        e->device_counted = true;
+    }
     if (int rc_ = drain_host(e)) return rc_;
     BatchArgs a = base_args(e);
     a.actions = actions;
-    const LaunchOpts o = make_opts(e, step_flags);
+    LaunchOpts o = make_opts(e, step_flags);
+    // device-counted steps read the counter after a grid-wide dependency: no chained launches
+    if (e->device_counted && o.pdl == 2) o.pdl = 1;
     // Chained launch: this step may skip the grid-wide dependency on the previous launch when the
     // handle's per-CTA flags describe its current state for exactly this CTA -> env mapping.
     const int fe = (int)flag_envs(a, o);
@@ -636,7 +692,13 @@ int gymrs_step_host_async(gymrs_env *e, const void *actions, uint32_t step_flags
                           float *obs, float *reward, uint8_t *done, uint8_t *truncated, uint64_t *ticket)
 {
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    if (int rc_ = refuse_in_capture(e, "gymrs_step_host")) return rc_;
     ON_DEVICE(e->device);
+    if (e->device_counted && !e->host_inflight) {
+        // host steps are sliced into several launches that must share one epoch: count on the
+        // host for the duration (the kernels keep recording the count on the device)
+        if (int rc_ = refresh_step_count(e)) return rc_;
+    }
     const uint64_t n = e->n;
     const uint64_t tk = e->host_seq;
     const int par = (int)(tk & 1);
@@ -681,6 +743,7 @@ int gymrs_step_host_async(gymrs_env *e, const void *actions, uint32_t step_flags
         // the result rows of chunk c are still being copied out for host step tk - 1
         if (e->host_inflight) CU(cudaStreamWaitEvent(cs, copied, 0));
         BatchArgs a = slice_args(e, b, cnt);
+        a.epoch_from_dev = 0;
         a.actions = staging + 4 * b;
         CU(do_step(e, a, o, cs, false));
         CU(cudaEventRecord(out_ready, cs));
@@ -738,6 +801,10 @@ int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t 
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     if (n_steps == 0) return GYMRS_OK;
     ON_DEVICE(e->device);
+    if (capturing(e)) {
+        if (e->host_inflight) return fail(GYMRS_ERR_UNSUPPORTED, "a host step is in flight: gymrs_host_wait before capturing");
+        e->device_counted = true;
+    }
     if (int rc_ = drain_host(e)) return rc_;
     BatchArgs a = base_args(e);
     a.actions = actions;
@@ -756,6 +823,7 @@ int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t 
 int gymrs_get_state(gymrs_env *e, float *state, int32_t *sbt)
 {
     if (!e || !state) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    if (int rc_ = refuse_in_capture(e, "gymrs_get_state")) return rc_;
     ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
     CU(cudaMemcpy2DAsync(state, sizeof(float) * e->n, e->state, sizeof(float) * e->ld,
@@ -771,6 +839,7 @@ int gymrs_get_state(gymrs_env *e, float *state, int32_t *sbt)
 int gymrs_set_state(gymrs_env *e, const float *state, const int32_t *sbt)
 {
     if (!e || !state) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    if (int rc_ = refuse_in_capture(e, "gymrs_set_state")) return rc_;
     ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
     e->chain_ok = false;
@@ -901,8 +970,10 @@ int gymrs_checkpoint_save(gymrs_env *e, void *buf, size_t bytes)
     if (!e || !buf) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     const CkptLayout l = ckpt_layout(e->kind, e->n, e->flags);
     if (bytes < l.total) return fail(GYMRS_ERR_BAD_ARG, "checkpoint buffer too small (see gymrs_checkpoint_size)");
+    if (int rc_ = refuse_in_capture(e, "gymrs_checkpoint_save")) return rc_;
     ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
+    if (int rc_ = refresh_step_count(e)) return rc_;
     unsigned char *out = (unsigned char *)buf;
     std::memset(out, 0, l.total); // section padding is part of the checksum
     const uint64_t n = e->n;
@@ -949,6 +1020,7 @@ int gymrs_checkpoint_load(gymrs_env *e, const void *buf, size_t bytes)
     if (h.n != e->n) return fail(GYMRS_ERR_BAD_ARG, "checkpoint holds a different number of envs");
     if ((h.flags ^ e->flags) & GYMRS_FLAG_TIME_LIMIT)
         return fail(GYMRS_ERR_BAD_ARG, "checkpoint and handle differ in GYMRS_FLAG_TIME_LIMIT");
+    if (int rc_ = refuse_in_capture(e, "gymrs_checkpoint_load")) return rc_;
     ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
     const CkptLayout l = ckpt_layout(e->kind, e->n, e->flags);
@@ -966,6 +1038,8 @@ int gymrs_checkpoint_load(gymrs_env *e, const void *buf, size_t bytes)
     CU(cudaMemcpyAsync(e->truncated, in + l.truncated, n, cudaMemcpyHostToDevice, s));
     if (l.sbt) CU(cudaMemcpyAsync(e->sbt, in + l.sbt, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
     if (l.elapsed) CU(cudaMemcpyAsync(e->elapsed, in + l.elapsed, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->epoch_mem, &h.step_count, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->epoch_mem + 2, &h.seed, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));
     e->global_off = h.global_off;
     e->seed = h.seed;
@@ -1074,6 +1148,7 @@ int gymrs_kind_of(const gymrs_env *e, int *kind)
 int gymrs_sync(gymrs_env *e, uint64_t *bad_env)
 {
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
+    if (int rc_ = refuse_in_capture(e, "gymrs_sync")) return rc_;
     ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
     CU(cudaStreamSynchronize(e->stream));
@@ -1082,6 +1157,11 @@ int gymrs_sync(gymrs_env *e, uint64_t *bad_env)
         e->chain_ok = false;
         CU(cudaMemsetAsync(e->chain_mem, 0, sizeof(uint32_t), e->stream));
         return fail(GYMRS_ERR_CUDA, "chained step launch timed out waiting for the previous step (pdl = 2 protocol error)");
+    }
+    if (e->err_host[5]) {
+        e->err_host[5] = 0;
+        return fail(GYMRS_ERR_UNSUPPORTED, "a CUDA graph whose steps were captured under a different seed was replayed: "
+                    "captured steps bake the handle's Philox key in, so re-capture after re-seeding the handle");
     }
     if (e->err_host[0]) {
         const uint64_t gid = (uint64_t)e->err_host[1] | ((uint64_t)e->err_host[2] << 32);

@@ -131,6 +131,39 @@ __device__ __forceinline__ void report_invalid(uint32_t *err, uint64_t gid, uint
     *reinterpret_cast<volatile uint32_t *>(err) = 1u;
 }
 
+// ---- step counter on the device (BatchArgs::epoch_dev) ----------------------------
+// Host-counted launches only record the count (one store per grid) so that a later graph replay
+// starts from the right value; device-counted launches read it once the previous grid is done ...
+__device__ __forceinline__ uint64_t first_epoch(const BatchArgs &a)
+{
+    if (!a.epoch_from_dev) return a.epoch;
+    // epoch_dev[2] is the seed of the handle's last full reset.  The Philox keys of this launch were
+    // frozen when it was captured; if the handle has been re-seeded since, the replay would draw
+    // from the old stream -- raise the sticky error word (gymrs_sync reports it) instead.
+    if (blockIdx.x == 0 && threadIdx.x == 0 &&
+        __ldcg(a.epoch_dev + 2) != ((uint64_t)a.rk.k[0][0] | ((uint64_t)a.rk.k[0][1] << 32)))
+        *reinterpret_cast<volatile uint32_t *>(a.err + 5) = 1u;
+    return __ldcg(a.epoch_dev) + 1u;
+}
+// ... and the last CTA of the grid to get here advances it.  Every thread of the CTA has read the
+// counter before the barrier, and the next device-counted launch reads it only after this grid
+// has completed (it never skips the grid-wide dependency), so the plain store is race-free.
+__device__ __forceinline__ void finish_epoch(const BatchArgs &a, uint64_t first, uint32_t n_steps, bool recorder)
+{
+    if (a.epoch_from_dev) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t *arrived = reinterpret_cast<uint32_t *>(a.epoch_dev + 1);
+            if (atomicAdd(arrived, 1u) == gridDim.x - 1) {
+                *arrived = 0u;
+                *a.epoch_dev = first - 1u + n_steps;
+            }
+        }
+    } else if (recorder && a.epoch_dev) {
+        *a.epoch_dev = first - 1u + n_steps;
+    }
+}
+
 // ---- one transition of the V envs a thread owns, all on registers ------------
 template <class E, int V, bool AR, bool SBT, bool TL>
 __device__ __forceinline__ void transition(const typename E::P &p, const BatchArgs &a,
@@ -210,7 +243,7 @@ __device__ __forceinline__ void transition(const typename E::P &p, const BatchAr
 
 template <class E, int V, bool AR, bool SBT, bool TL, bool FULL>
 __device__ __forceinline__ void step_body(const typename E::P &p, const BatchArgs &a, uint64_t i0,
-                                          int nvalid, typename E::Action (&act)[V])
+                                          int nvalid, typename E::Action (&act)[V], uint64_t epoch)
 {
     float s[E::SD][V], o[E::OD][V];
 #pragma unroll
@@ -222,7 +255,7 @@ __device__ __forceinline__ void step_body(const typename E::P &p, const BatchArg
 
     float rew[V];
     uint8_t dn[V], tr[V];
-    transition<E, V, AR, SBT, TL>(p, a, s, o, act, sbt, el, rew, dn, tr, a.global_off + i0, a.epoch, nvalid);
+    transition<E, V, AR, SBT, TL>(p, a, s, o, act, sbt, el, rew, dn, tr, a.global_off + i0, epoch, nvalid);
 
 #pragma unroll
     for (int r = 0; r < E::SD; ++r) st_row<V, FULL>(a.state + r * a.ld + i0, s[r], nvalid);
@@ -300,14 +333,16 @@ step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Bat
         pdl_wait();
     }
 
+    const uint64_t epoch = first_epoch(a);
     if (live) {
         if (!a.early_actions) {
             if (full) ld_stream<V, true>(actp, act, nvalid);
             else ld_stream<V, false>(actp, act, nvalid);
         }
-        if (full) step_body<E, V, AR, SBT, TL, true>(p, a, i0, nvalid, act);
-        else step_body<E, V, AR, SBT, TL, false>(p, a, i0, nvalid, act);
+        if (full) step_body<E, V, AR, SBT, TL, true>(p, a, i0, nvalid, act, epoch);
+        else step_body<E, V, AR, SBT, TL, false>(p, a, i0, nvalid, act, epoch);
     }
+    finish_epoch(a, epoch, 1u, blockIdx.x == 0 && threadIdx.x == 0);
 
     // publish "this CTA's envs are at step chain_seq" for the next chained launch.  The barrier
     // orders every thread's stores before thread 0's release (cumulativity), so one release store
@@ -487,6 +522,7 @@ step_stream_kernel(const __grid_constant__ typename E::P p, const __grid_constan
             // the mbarrier hand-over orders every compute thread's stores before this release
             if (a.publish) st_release_gpu(a.chain_flags + tile_of(k), a.chain_seq);
         }
+        if (blockIdx.x == 0 && a.epoch_dev) *a.epoch_dev = a.epoch; // host-counted only (dispatch_vec)
         return;
     }
 
@@ -535,7 +571,8 @@ step_stream_kernel(const __grid_constant__ typename E::P p, const __grid_constan
 // reads one action row and streams out observation / reward / done.  The actions of
 // step k+1 are loaded before the math of step k so their latency is covered.
 template <class E, int V, bool AR, bool SBT, bool TL, bool FULL>
-__device__ __forceinline__ void rollout_body(const typename E::P &p, const BatchArgs &a, uint64_t i0, int nvalid)
+__device__ __forceinline__ void rollout_body(const typename E::P &p, const BatchArgs &a, uint64_t i0, int nvalid,
+                                             uint64_t epoch)
 {
     using A = typename E::Action;
     const A *actp = reinterpret_cast<const A *>(a.actions) + i0;
@@ -555,7 +592,7 @@ __device__ __forceinline__ void rollout_body(const typename E::P &p, const Batch
     for (uint32_t k = 0; k < a.n_steps; ++k) {
         if (k + 1 < a.n_steps) ld_stream<V, FULL>(actp + (uint64_t)(k + 1) * a.act_ld, act_next, nvalid);
         transition<E, V, AR, SBT, TL>(p, a, s, o, act, sbt, el, rew, dn, tr, a.global_off + i0,
-                                      a.epoch + k, nvalid);
+                                      epoch + k, nvalid);
         if (a.obs_out) {
             float *ob = a.obs_out + (uint64_t)k * E::OD * a.out_ld + i0;
 #pragma unroll
@@ -588,9 +625,10 @@ __global__ void __launch_bounds__(256)
 rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ BatchArgs a)
 {
     const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
-    if (i0 >= a.n) return;
-    if (i0 + V <= a.n) rollout_body<E, V, AR, SBT, TL, true>(p, a, i0, V);
-    else rollout_body<E, V, AR, SBT, TL, false>(p, a, i0, (int)(a.n - i0));
+    const uint64_t epoch = first_epoch(a);
+    if (i0 + V <= a.n) rollout_body<E, V, AR, SBT, TL, true>(p, a, i0, V, epoch);
+    else if (i0 < a.n) rollout_body<E, V, AR, SBT, TL, false>(p, a, i0, (int)(a.n - i0), epoch);
+    finish_epoch(a, epoch, a.n_steps, blockIdx.x == 0 && threadIdx.x == 0);
 }
 
 // ---- reset ----------------------------------------------------------------------
@@ -601,6 +639,10 @@ reset_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Ba
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
+    if (i == 0 && !mask) { // a full reset restarts the handle's step counter under this seed
+        a.epoch_dev[0] = 0;
+        a.epoch_dev[2] = (uint64_t)a.rk.k[0][0] | ((uint64_t)a.rk.k[0][1] << 32);
+    }
     if (mask && !mask[i]) return;
     float s[E::SD], o[E::OD];
     E::reset(p, s, o, reset_words(a.rk, a.global_off + i, 0));
@@ -728,7 +770,7 @@ template <class E, bool ROLLOUT>
 cudaError_t dispatch_vec(const typename E::P &p, const BatchArgs &a, const LaunchOpts &o, cudaStream_t s)
 {
     if (a.n == 0) return cudaSuccess;
-    if (!ROLLOUT && use_tma_step(a, o)) return dispatch_tma<E>(p, a, o, s);
+    if (!ROLLOUT && use_tma_step(a, o) && !a.epoch_from_dev) return dispatch_tma<E>(p, a, o, s);
     switch (pick_vec(a, o.vec, ROLLOUT)) {
     case 4: return dispatch_flags<E, 4, ROLLOUT>(p, a, o, s);
     case 2: return dispatch_flags<E, 2, ROLLOUT>(p, a, o, s);
