@@ -311,8 +311,9 @@ def run_b200(args):
         wall.append((time.perf_counter() - w0) * 1e3)
         ms = ev0.elapsed_time(ev1)
         # the device time must account for the host wall time of the same region (launch until
-        # drained); if it does not, the events were not on the stream the kernels ran on
-        assert ms > 0.7 * wall[-1] or wall[-1] < 0.2, (ms, wall[-1])
+        # drained); if it does not, the events were not on the stream the kernels ran on.  Regions
+        # shorter than 1 ms are dominated by the fixed cost of the two barriers and are not judged.
+        assert ms > 0.7 * wall[-1] or wall[-1] < 1.0, (ms, wall[-1])
         if world > 1:
             t = torch.tensor([ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
