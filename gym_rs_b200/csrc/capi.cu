@@ -303,6 +303,9 @@ int drain_host(gymrs_env *e)
     return GYMRS_OK;
 }
 
+// host-counted launches on a device-counted handle (the sliced host step) publish the new count
+__global__ void set_step_count_kernel(uint64_t *epoch_mem, uint64_t count) { epoch_mem[0] = count; }
+
 // Is the handle's stream being captured into a CUDA graph?  (The legacy default stream cannot be.)
 bool capturing(const gymrs_env *e)
 {
@@ -321,6 +324,30 @@ int refuse_in_capture(const gymrs_env *e, const char *what)
     if (!capturing(e)) return GYMRS_OK;
     return fail(GYMRS_ERR_UNSUPPORTED, std::string(what) + " cannot be captured into a CUDA graph "
                 "(only gymrs_step, gymrs_rollout and a seeded full gymrs_reset can)");
+}
+
+// The first time a step of this handle is recorded into a graph, hand the step count over to the
+// device.  The handle's stream is capturing, so the hand-over runs on a side stream: nothing
+// queued earlier on the handle's stream touches the device counter (host-counted launches ignore
+// it), and every replay is launched after this function has returned.  Synchronising calls are
+// off limits while any stream captures in the default (global) capture mode, hence the relaxed
+// mode for the duration -- the same thing torch's allocator does around its event queries.
+int begin_device_counting(gymrs_env *e)
+{
+    if (e->device_counted) return GYMRS_OK;
+    if (e->host_inflight) return fail(GYMRS_ERR_UNSUPPORTED, "a host step is in flight: gymrs_host_wait before capturing");
+    uint64_t *stage = reinterpret_cast<uint64_t *>(e->err_host + 8);
+    stage[0] = e->step_count;
+    stage[1] = 0; // CTA arrival counter
+    stage[2] = e->seed;
+    cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+    CU(cudaThreadExchangeStreamCaptureMode(&mode));
+    cudaError_t ce = cudaMemcpyAsync(e->epoch_mem, stage, 3 * sizeof(uint64_t), cudaMemcpyHostToDevice, e->copy_streams[0]);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->copy_streams[0]);
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    if (ce != cudaSuccess) return cuda_fail(ce, "handing the step counter over to the device");
+    e->device_counted = true;
+    return GYMRS_OK;
 }
 
 // Bring the host's step_count up to date with the device copy (synchronises the stream).
@@ -398,8 +425,8 @@ int alloc_env(gymrs_env *e)
     CU(cudaMemsetAsync(e->chain_mem, 0, chain_words * sizeof(uint32_t), e->stream));
     CU(cudaMalloc(&e->epoch_mem, 4 * sizeof(uint64_t)));
     CU(cudaMemsetAsync(e->epoch_mem, 0, 4 * sizeof(uint64_t), e->stream));
-    CU(cudaHostAlloc(&e->err_host, 8 * sizeof(uint32_t), cudaHostAllocMapped));
-    std::memset(e->err_host, 0, 8 * sizeof(uint32_t));
+    CU(cudaHostAlloc(&e->err_host, 16 * sizeof(uint32_t), cudaHostAllocMapped)); // [8..13]: staging, begin_device_counting
+    std::memset(e->err_host, 0, 16 * sizeof(uint32_t));
     CU(cudaHostGetDevicePointer(&e->err_dev, e->err_host, 0));
     return GYMRS_OK;
 }
@@ -499,6 +526,7 @@ int gymrs_create(int kind, uint64_t num_envs, int device, uint64_t global_env_of
     }
     // ::new samples an initial state from an entropy-seeded RNG (cartpole.rs:92,120)
     rc = gymrs_reset(e, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc == GYMRS_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(GYMRS_ERR_CUDA, "initial reset failed");
     if (rc != GYMRS_OK) {
         std::string msg = g_last_error;
         free_env(e);
@@ -615,7 +643,8 @@ int gymrs_reset(gymrs_env *e, const uint64_t *seed, const float *low, const floa
     ON_DEVICE(e->device);
     const bool cap = capturing(e);
     if (cap && (!seed || mask)) return fail(GYMRS_ERR_UNSUPPORTED, "only a seeded full gymrs_reset can be captured into a CUDA graph");
-    if (cap && e->host_inflight) return fail(GYMRS_ERR_UNSUPPORTED, "a host step is in flight: gymrs_host_wait before capturing");
+    if (cap)
+        if (int rc_ = begin_device_counting(e)) return rc_;
     if (int rc_ = drain_host(e)) return rc_;
     const uint64_t s = seed ? *seed : entropy64(); // seeding.rs:22
     if (seed_used) *seed_used = s;
@@ -643,7 +672,7 @@ int gymrs_reset(gymrs_env *e, const uint64_t *seed, const float *low, const floa
     fold_params(e);
     if (ce != cudaSuccess) return cuda_fail(ce, "reset launch");
     if (!mask) { // a full reset restarts the handle's auto-reset stream
-        e->seed = s; // the reset kernel also zeroes the device step counter and records the seed
+        e->seed = s; // on a device-counted handle the reset kernel also zeroes the device counter and records the seed
         e->step_count = 0;
         e->sbt_dirty = false;
     }
@@ -654,10 +683,8 @@ int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
 {
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     ON_DEVICE(e->device);
-    if (capturing(e)) {
-        if (e->host_inflight) return fail(GYMRS_ERR_UNSUPPORTED, "a host step is in flight: gymrs_host_wait before capturing");
-        e->device_counted = true;
-    }
+    if (capturing(e))
+        if (int rc_ = begin_device_counting(e)) return rc_;
     if (int rc_ = drain_host(e)) return rc_;
     BatchArgs a = base_args(e);
     a.actions = actions;
@@ -758,6 +785,10 @@ int gymrs_step_host_async(gymrs_env *e, const void *actions, uint32_t step_flags
     }
     CU(cudaEventRecord(e->hev[HostEv::host_done(par)], d2h));
     after_step(e, step_flags, 1);
+    if (e->device_counted) {
+        set_step_count_kernel<<<1, 1, 0, cs>>>(e->epoch_mem, e->step_count);
+        CU(cudaGetLastError());
+    }
     e->host_inflight = true;
     e->host_seq = tk + 1;
     if (ticket) *ticket = tk;
@@ -801,10 +832,8 @@ int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t 
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     if (n_steps == 0) return GYMRS_OK;
     ON_DEVICE(e->device);
-    if (capturing(e)) {
-        if (e->host_inflight) return fail(GYMRS_ERR_UNSUPPORTED, "a host step is in flight: gymrs_host_wait before capturing");
-        e->device_counted = true;
-    }
+    if (capturing(e))
+        if (int rc_ = begin_device_counting(e)) return rc_;
     if (int rc_ = drain_host(e)) return rc_;
     BatchArgs a = base_args(e);
     a.actions = actions;

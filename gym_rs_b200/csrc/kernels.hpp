@@ -27,10 +27,11 @@ struct BatchArgs {
     PhiloxKeys rk;       // Philox round keys of the handle's seed (philox_round_keys)
     uint64_t epoch;      // Philox counter high half for auto-resets in this step (rollout: first step)
     // Device copy of the handle's step counter: epoch_dev[0] = steps since the last full reset,
-    // low word of epoch_dev[1] = CTA arrival counter, epoch_dev[2] = seed of that reset.  epoch_from_dev == 0: the kernel uses `epoch`
-    // (counted on the host) and records the new count; == 1: the kernel reads the count itself after
-    // its dependency wait and the last CTA to finish advances it -- the form a CUDA graph needs,
-    // where kernel arguments are frozen at capture but every replay is a new step.
+    // low word of epoch_dev[1] = CTA arrival counter, epoch_dev[2] = seed of that reset.
+    // epoch_from_dev == 0: the kernel uses `epoch` (counted on the host) and never touches the
+    // device copy; == 1: the kernel reads the count itself after its dependency wait and the last
+    // CTA to finish advances it -- the form a CUDA graph needs, where kernel arguments are frozen
+    // at capture but every replay is a new step.
     uint64_t *epoch_dev;
     int epoch_from_dev;
     uint32_t *err;       // device-visible words: [0] invalid-action flag, [1..2] one offending global id,

@@ -132,11 +132,15 @@ __device__ __forceinline__ void report_invalid(uint32_t *err, uint64_t gid, uint
 }
 
 // ---- step counter on the device (BatchArgs::epoch_dev) ----------------------------
-// Host-counted launches only record the count (one store per grid) so that a later graph replay
-// starts from the right value; device-counted launches read it once the previous grid is done ...
+// DEVC = false (every eager launch of a handle that was never captured): the epoch is the kernel
+// argument the host counted; the device copy is not touched and the code below compiles away.
+// DEVC = true (the handle's steps have been captured into a CUDA graph, where kernel arguments
+// are frozen but every replay is a new step): the launch reads the count once the previous grid
+// is done ...
+template <bool DEVC>
 __device__ __forceinline__ uint64_t first_epoch(const BatchArgs &a)
 {
-    if (!a.epoch_from_dev) return a.epoch;
+    if constexpr (!DEVC) return a.epoch;
     // epoch_dev[2] is the seed of the handle's last full reset.  The Philox keys of this launch were
     // frozen when it was captured; if the handle has been re-seeded since, the replay would draw
     // from the old stream -- raise the sticky error word (gymrs_sync reports it) instead.
@@ -148,9 +152,10 @@ __device__ __forceinline__ uint64_t first_epoch(const BatchArgs &a)
 // ... and the last CTA of the grid to get here advances it.  Every thread of the CTA has read the
 // counter before the barrier, and the next device-counted launch reads it only after this grid
 // has completed (it never skips the grid-wide dependency), so the plain store is race-free.
-__device__ __forceinline__ void finish_epoch(const BatchArgs &a, uint64_t first, uint32_t n_steps, bool recorder)
+template <bool DEVC>
+__device__ __forceinline__ void finish_epoch(const BatchArgs &a, uint64_t first, uint32_t n_steps)
 {
-    if (a.epoch_from_dev) {
+    if constexpr (DEVC) {
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t *arrived = reinterpret_cast<uint32_t *>(a.epoch_dev + 1);
@@ -159,8 +164,6 @@ __device__ __forceinline__ void finish_epoch(const BatchArgs &a, uint64_t first,
                 *a.epoch_dev = first - 1u + n_steps;
             }
         }
-    } else if (recorder && a.epoch_dev) {
-        *a.epoch_dev = first - 1u + n_steps;
     }
 }
 
@@ -270,7 +273,7 @@ __device__ __forceinline__ void step_body(const typename E::P &p, const BatchArg
     if (TL) st_row<V, FULL>(a.elapsed + i0, el, nvalid);
 }
 
-template <class E, int V, bool AR, bool SBT, bool TL>
+template <class E, int V, bool AR, bool SBT, bool TL, bool DEVC>
 __global__ void __launch_bounds__(256, GYMRS_STEP_MIN_CTAS)
 step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ BatchArgs a)
 {
@@ -333,7 +336,7 @@ step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Bat
         pdl_wait();
     }
 
-    const uint64_t epoch = first_epoch(a);
+    const uint64_t epoch = first_epoch<DEVC>(a);
     if (live) {
         if (!a.early_actions) {
             if (full) ld_stream<V, true>(actp, act, nvalid);
@@ -342,7 +345,7 @@ step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Bat
         if (full) step_body<E, V, AR, SBT, TL, true>(p, a, i0, nvalid, act, epoch);
         else step_body<E, V, AR, SBT, TL, false>(p, a, i0, nvalid, act, epoch);
     }
-    finish_epoch(a, epoch, 1u, blockIdx.x == 0 && threadIdx.x == 0);
+    finish_epoch<DEVC>(a, epoch, 1u);
 
     // publish "this CTA's envs are at step chain_seq" for the next chained launch.  The barrier
     // orders every thread's stores before thread 0's release (cumulativity), so one release store
@@ -522,7 +525,6 @@ step_stream_kernel(const __grid_constant__ typename E::P p, const __grid_constan
             // the mbarrier hand-over orders every compute thread's stores before this release
             if (a.publish) st_release_gpu(a.chain_flags + tile_of(k), a.chain_seq);
         }
-        if (blockIdx.x == 0 && a.epoch_dev) *a.epoch_dev = a.epoch; // host-counted only (dispatch_vec)
         return;
     }
 
@@ -620,15 +622,15 @@ __device__ __forceinline__ void rollout_body(const typename E::P &p, const Batch
     if (TL) st_row<V, FULL>(a.elapsed + i0, el, nvalid);
 }
 
-template <class E, int V, bool AR, bool SBT, bool TL>
+template <class E, int V, bool AR, bool SBT, bool TL, bool DEVC>
 __global__ void __launch_bounds__(256)
 rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ BatchArgs a)
 {
     const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
-    const uint64_t epoch = first_epoch(a);
+    const uint64_t epoch = first_epoch<DEVC>(a);
     if (i0 + V <= a.n) rollout_body<E, V, AR, SBT, TL, true>(p, a, i0, V, epoch);
     else if (i0 < a.n) rollout_body<E, V, AR, SBT, TL, false>(p, a, i0, (int)(a.n - i0), epoch);
-    finish_epoch(a, epoch, a.n_steps, blockIdx.x == 0 && threadIdx.x == 0);
+    finish_epoch<DEVC>(a, epoch, a.n_steps);
 }
 
 // ---- reset ----------------------------------------------------------------------
@@ -639,7 +641,7 @@ reset_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Ba
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    if (i == 0 && !mask) { // a full reset restarts the handle's step counter under this seed
+    if (i == 0 && !mask && a.epoch_from_dev) { // a full reset restarts the device step counter under this seed
         a.epoch_dev[0] = 0;
         a.epoch_dev[2] = (uint64_t)a.rk.k[0][0] | ((uint64_t)a.rk.k[0][1] << 32);
     }
@@ -677,7 +679,7 @@ cudaError_t launch_ex(K kernel, uint64_t threads, int block, bool pdl, cudaStrea
     return cudaLaunchKernelEx(&cfg, kernel, p, a);
 }
 
-template <class E, int V, bool ROLLOUT>
+template <class E, int V, bool ROLLOUT, bool DEVC>
 cudaError_t dispatch_flags(const typename E::P &p, const BatchArgs &a_in, const LaunchOpts &o, cudaStream_t s)
 {
     const uint64_t threads = (a_in.n + V - 1) / V;
@@ -689,8 +691,8 @@ cudaError_t dispatch_flags(const typename E::P &p, const BatchArgs &a_in, const 
     const int key = (o.autoreset ? 4 : 0) | (sbt ? 2 : 0) | (o.time_limit ? 1 : 0);
 #define GYMRS_CASE(K, AR, SB, TL)                                                                   \
     case K:                                                                                         \
-        return ROLLOUT ? launch_ex(rollout_kernel<E, V, AR, SB, TL>, threads, block, false, s, p, a) \
-                       : launch_ex(step_kernel<E, V, AR, SB, TL>, threads, block, o.pdl != 0, s, p, a);
+        return ROLLOUT ? launch_ex(rollout_kernel<E, V, AR, SB, TL, DEVC>, threads, block, false, s, p, a) \
+                       : launch_ex(step_kernel<E, V, AR, SB, TL, DEVC>, threads, block, o.pdl != 0, s, p, a);
     switch (key) {
         GYMRS_CASE(0, false, false, false)
         GYMRS_CASE(1, false, false, true)
@@ -771,10 +773,15 @@ cudaError_t dispatch_vec(const typename E::P &p, const BatchArgs &a, const Launc
 {
     if (a.n == 0) return cudaSuccess;
     if (!ROLLOUT && use_tma_step(a, o) && !a.epoch_from_dev) return dispatch_tma<E>(p, a, o, s);
-    switch (pick_vec(a, o.vec, ROLLOUT)) {
-    case 4: return dispatch_flags<E, 4, ROLLOUT>(p, a, o, s);
-    case 2: return dispatch_flags<E, 2, ROLLOUT>(p, a, o, s);
-    default: return dispatch_flags<E, 1, ROLLOUT>(p, a, o, s);
+    const int v = pick_vec(a, o.vec, ROLLOUT);
+    if (a.epoch_from_dev) { // device-counted (CUDA-graph) launches: the 128-bit path or the scalar one
+        if (v == 4) return dispatch_flags<E, 4, ROLLOUT, true>(p, a, o, s);
+        return dispatch_flags<E, 1, ROLLOUT, true>(p, a, o, s);
+    }
+    switch (v) {
+    case 4: return dispatch_flags<E, 4, ROLLOUT, false>(p, a, o, s);
+    case 2: return dispatch_flags<E, 2, ROLLOUT, false>(p, a, o, s);
+    default: return dispatch_flags<E, 1, ROLLOUT, false>(p, a, o, s);
     }
 }
 

@@ -2,8 +2,11 @@
    pool = 'ring' (16 cold 1M-env batches round-robin) or 'resident' (one batch, L2-resident)
    scheme = eager pdl 0/1/2, or a CUDA graph of `span` captured steps (device-counted, pdl 1 edges)
 Usage: python tools/exp_modes.py [env] [n_envs]"""
+import os
 import statistics
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 
