@@ -261,7 +261,12 @@ LaunchOpts make_opts(const gymrs_env *e, uint32_t step_flags)
     o.use_sbt = e->kind == GYMRS_CARTPOLE && (!o.autoreset || e->sbt_dirty);
     o.pdl = e->pdl;
     o.vec = e->vec;
+    // CTA size of a step launch.  128 threads (10 CTAs per SM instead of 5, twice as many progress
+    // flags) measured 1 % faster than 256 on the two-stream ring and 3-8 % faster for chained and
+    // L2-resident launches for CartPole and MountainCar; Pendulum is 1 % faster at 256
+    // (profiles/r01_sweeps.md).  The persistent kernel (vec = 8) has its own fixed geometry.
     o.block = e->block;
+    if (o.block == 0 && o.vec != 8) o.block = e->kind == GYMRS_PENDULUM ? 256 : 128;
     return o;
 }
 
@@ -844,7 +849,9 @@ int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t 
     a.reward_out = reward_out;
     a.done_out = done_out;
     e->chain_ok = false;
-    CU(do_step(e, a, make_opts(e, step_flags), e->stream, true));
+    LaunchOpts o = make_opts(e, step_flags);
+    if (e->block == 0) o.block = 256; // the rollout keeps its state in registers: 62 of them, 4 CTAs of 256 per SM
+    CU(do_step(e, a, o, e->stream, true));
     after_step(e, step_flags, n_steps);
     return GYMRS_OK;
 }

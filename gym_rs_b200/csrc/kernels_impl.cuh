@@ -375,7 +375,7 @@ step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Bat
 // L2-resident (a tile is worked on by only 8 warps) -- hence opt-in.
 constexpr int TMA_TILE = 1024; // envs per tile = 256 threads x 4
 #ifndef GYMRS_STREAM_STAGES
-#define GYMRS_STREAM_STAGES 3
+#define GYMRS_STREAM_STAGES 2 // measured, one stream chained, CartPole: 2 stages 7.5 us, 3: 8.1, 4: 9.8 (profiles/r01_sweeps.md)
 #endif
 constexpr int STREAM_STAGES = GYMRS_STREAM_STAGES;
 
