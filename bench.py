@@ -28,6 +28,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's banner / debug lines (NCCL_DEBUG set on the box) go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 N_ENVS = 1 << 20
 RING = 16

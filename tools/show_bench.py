@@ -1,7 +1,7 @@
 import json,sys
 tag=sys.argv[1]
 try:
-    d=json.loads(sys.stdin.read())
+    d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{')][-1])
     r=d.get("rollout") or {}
     c=d.get("single_stream_chained") or {}
     e=d.get("e2e") or {}
