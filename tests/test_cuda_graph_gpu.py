@@ -77,7 +77,8 @@ def test_replayed_graph_equals_eager_steps(torch, g, kind, time_limit):
     for r in range(R):
         slots.copy_(all_actions[r * K:(r + 1) * K])
         torch.cuda.synchronize()
-        graph.replay()
+        with torch.cuda.stream(side):      # replay on the handle's stream: env.sync() then covers it
+            graph.replay()
         for k in range(K):
             eager.step(all_actions[r * K + k], autoreset=True)
         for a, b in zip(outputs(env), outputs(eager)):
@@ -128,7 +129,9 @@ def test_captured_reset_and_rollout(torch, g):
     ref.sync()
     for _ in range(2):                     # every replay restarts from the same seeded reset
         obs_out.zero_()
-        graph.replay()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(obs_out, ref_obs)
         assert np.array_equal(env.get_state(), ref.get_state())
@@ -149,15 +152,14 @@ def test_replay_after_reseeding_is_reported_not_silently_wrong(torch, g):
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph, stream=side):
         env.step(acts[0], autoreset=True)
-    graph.replay()
-    env.sync()
     with torch.cuda.stream(side):
-        env.reset(seed=2)       # the captured step still holds seed 1's Philox keys
-    graph.replay()
-    with pytest.raises(_capi.GymrsError, match="different seed"):
+        graph.replay()
         env.sync()
-    with torch.cuda.stream(side):
+        env.reset(seed=2)       # the captured step still holds seed 1's Philox keys
+        graph.replay()
+        with pytest.raises(_capi.GymrsError, match="different seed"):
+            env.sync()
         env.reset(seed=1)
-    graph.replay()
-    env.sync()                  # same seed again: fine
+        graph.replay()
+        env.sync()              # same seed again: fine
     env.close()

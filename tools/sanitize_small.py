@@ -36,4 +36,40 @@ for cls, hi in ((g.CartPoleEnv, 2), (g.MountainCarEnv, 3), (g.PendulumEnv, 0)):
         env.sync()
         assert np.isfinite(env.get_state()).all()
         env.close()
+# device-counted kernel variants (CUDA-graph capture): captured steps + rollout + seeded reset,
+# replayed, then an eager step, a host step, a checkpoint round trip and a clone on the same handle
+side = torch.cuda.Stream()
+for cls, hi in ((g.CartPoleEnv, 2), (g.PendulumEnv, 0)):
+    env = cls(num_envs=n, time_limit=True)
+    env.reset(seed=3)
+    if hi:
+        acts = torch.randint(0, hi, (4, n), generator=gen, device="cuda", dtype=torch.int32)
+    else:
+        acts = torch.rand((4, n), generator=gen, device="cuda") * 4 - 2
+    env.sync()
+    env.set_stream(side.cuda_stream)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        env.reset(seed=3)
+        for t in range(4):
+            env.step(acts[t], autoreset=True)
+        env.rollout(acts, autoreset=True)
+    with torch.cuda.stream(side):  # the handle's stream
+        for _ in range(3):
+            graph.replay()
+    env.step(acts[0], autoreset=True)
+    obs = np.empty((env.obs_dim, n), dtype=np.float32)
+    rew = np.empty(n, dtype=np.float32)
+    done = np.empty(n, dtype=np.uint8)
+    env.step_host(acts[1].cpu(), obs, rew, done, None, autoreset=True)
+    blob = env.checkpoint()
+    count = g.core.checkpoint_info(blob)["step_count"]
+    assert count == 10, count
+    twin = cls.from_checkpoint(blob)
+    other = env.clone()
+    twin.step(acts[2], autoreset=True)
+    other.step(acts[2], autoreset=True)
+    assert np.array_equal(twin.get_state(), other.get_state())
+    for e in (env, twin, other):
+        e.close()
 print("sanitize_small ok")
