@@ -2,7 +2,9 @@
 //
 // Philox4x32-10 (Salmon et al., SC'11): the same function as curand's
 // curand_Philox4x32_10, written out so that one call costs 20 IMAD.WIDE and no
-// state has to live in HBM.  The reference re-seeds a fresh PCG64 on every
+// state has to live in HBM.  reset_words(seed, gid, epoch) is bit-identical to
+// curand_init(seed, /*subsequence*/ epoch, /*offset*/ 4 * gid, &st); curand4(&st)
+// (tests/test_curand_gpu.py checks it against cuRAND's own device generator).  The reference re-seeds a fresh PCG64 on every
 // reset (cartpole.rs:491-494, mountain_car.rs:470-473, seeding.rs:21-26), i.e.
 // a reset is a pure function of the seed; here it is a pure function of
 // (seed, global env id, epoch), which keeps that property per env and makes
