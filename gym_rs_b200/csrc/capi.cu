@@ -850,7 +850,9 @@ int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t 
     a.done_out = done_out;
     e->chain_ok = false;
     LaunchOpts o = make_opts(e, step_flags);
-    if (e->block == 0) o.block = 256; // the rollout keeps its state in registers: 62 of them, 4 CTAs of 256 per SM
+    // measured (profiles/r01_sweeps.md): CartPole 209 G env-steps/s at 128 threads vs 200 G at 256;
+    // MountainCar 287 vs 305, Pendulum 236 vs 246
+    if (e->block == 0) o.block = e->kind == GYMRS_CARTPOLE ? 128 : 256;
     CU(do_step(e, a, o, e->stream, true));
     after_step(e, step_flags, n_steps);
     return GYMRS_OK;

@@ -223,7 +223,7 @@ int gymrs_sync(gymrs_env *env, uint64_t *bad_env);
  *      8 selects the persistent TMA-staged variant (cp.async.bulk into a shared-memory ring,
  *      4 envs per thread), which falls back to the plain kernel when alignment does not allow it.
  * block: threads per CTA, 0 = the library's choice (step: 128 for CartPole / MountainCar, 256 for
- *      Pendulum; rollout: 256), else a multiple of 32 up to 256.
+ *      Pendulum; rollout: 128 for CartPole, else 256), else a multiple of 32 up to 256.
  * pdl: 0 = plain stream order.
  *      1 (default) = programmatic dependent launch: the next step's CTAs are scheduled while the
  *        previous launch drains, but touch memory only after it has completed.
