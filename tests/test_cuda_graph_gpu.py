@@ -45,15 +45,20 @@ def outputs(env):
             env._t_done.cpu().numpy().copy(), env._t_truncated.cpu().numpy().copy()]
 
 
-@pytest.mark.parametrize("kind,time_limit", [("cartpole", False), ("cartpole", True), ("mountain_car", True),
-                                             ("pendulum", False)])
-def test_replayed_graph_equals_eager_steps(torch, g, kind, time_limit):
+@pytest.mark.parametrize("kind,time_limit,config", [
+    ("cartpole", False, None), ("cartpole", True, None), ("mountain_car", True, None), ("pendulum", False, None),
+    # opt-in launch schemes are demoted for captured steps: chained launches (pdl = 2) to a grid-wide
+    # dependency, the persistent TMA-staged kernel (vec = 8) to step_kernel; one lane per env stays
+    ("cartpole", False, (8, 0, 2)), ("pendulum", True, (1, 64, 2))])
+def test_replayed_graph_equals_eager_steps(torch, g, kind, time_limit, config):
     from gym_rs_b200 import _capi
     n = 200_000
     all_actions = random_actions(torch, kind, K * R + 4, n, 7)
     eager = make(g, kind, n, time_limit=time_limit)
     eager.reset(seed=11)
     env = make(g, kind, n, time_limit=time_limit)
+    if config:
+        env.set_launch_config(*config)
     env.reset(seed=11)
     # three eager steps first: the device counter must pick up where the host count stands
     for k in range(3):
