@@ -2,7 +2,7 @@
 use std::os::raw::c_void;
 
 use gym_rs::core::{ActionReward, Env, EnvProperties};
-use gym_rs::envs::classical_control::cartpole::CartPoleObservation;
+use gym_rs::envs::classical_control::cartpole::{CartPoleObservation, KinematicsIntegrator};
 use gym_rs::spaces::{BoxR, Discrete};
 use gym_rs::utils::custom::structs::Metadata;
 use gym_rs::utils::custom::types::O64;
@@ -31,6 +31,7 @@ pub struct CartPoleEnv {
     pub length: O64,
     pub force_mag: O64,
     pub tau: O64,
+    pub kinematics_integrator: KinematicsIntegrator,
     pub theta_threshold_radians: O64,
     pub x_threshold: O64,
     pub steps_beyond_terminated: Option<usize>,
@@ -79,6 +80,7 @@ impl CartPoleEnv {
             length: OrderedFloat(p.length),
             force_mag: OrderedFloat(p.force_mag),
             tau: OrderedFloat(p.tau),
+            kinematics_integrator: KinematicsIntegrator::Euler, // cartpole.rs:100
             theta_threshold_radians: OrderedFloat(p.theta_threshold_radians),
             x_threshold: OrderedFloat(p.x_threshold),
             steps_beyond_terminated: None,
@@ -99,6 +101,10 @@ impl CartPoleEnv {
         p.length = self.length.into_inner();
         p.force_mag = self.force_mag.into_inner();
         p.tau = self.tau.into_inner();
+        p.kinematics_integrator = match self.kinematics_integrator {
+            KinematicsIntegrator::Euler => 0,
+            KinematicsIntegrator::Other => 1, // cartpole.rs:437-441
+        };
         p.theta_threshold_radians = self.theta_threshold_radians.into_inner();
         p.x_threshold = self.x_threshold.into_inner();
         unsafe { ffi::check(ffi::gymrs_set_params(self.handle, &p as *const _ as *const c_void)) };
@@ -185,6 +191,7 @@ impl Clone for CartPoleEnv {
             length: self.length,
             force_mag: self.force_mag,
             tau: self.tau,
+            kinematics_integrator: self.kinematics_integrator.clone(),
             theta_threshold_radians: self.theta_threshold_radians,
             x_threshold: self.x_threshold,
             steps_beyond_terminated: self.steps_beyond_terminated,
