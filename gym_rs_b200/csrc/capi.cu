@@ -139,11 +139,16 @@ struct gymrs_env {
 
     uint64_t seed = 0;       // Philox key of the auto-reset stream
     uint64_t step_count = 0; // steps since the last full reset; epoch of an auto-reset = step_count + 1
-    // Device copy of step_count (+ a CTA arrival counter), see BatchArgs::epoch_dev.  Once a step of
-    // this handle has been captured into a CUDA graph the host can no longer count steps (replays
-    // happen behind its back): from then on the device copy is the authority (device_counted),
-    // kernels read and advance it themselves, and step_count is refreshed from it when needed.
+    // Device copies of step_count, see BatchArgs::epoch_dev.  Once a step of this handle has been
+    // captured into a CUDA graph the host can no longer count steps (replays happen behind its
+    // back): from then on the device copies are the authority (device_counted), every CTA of a
+    // launch reads and advances its own, and step_count is refreshed from copy 0 when needed.
+    // A launch of G CTAs advances copies [0, G) only.  Invariant between launches: the copies of
+    // the handle's canonical step geometry (canonical_ctas) are current; a launch with any other
+    // grid refreshes all copies from copy 0 before and after itself (spread_step_count), so the
+    // invariant holds whatever order graphs are replayed in.
     uint64_t *epoch_mem = nullptr;
+    uint64_t epoch_slots = 0;
     bool device_counted = false;
     bool sbt_dirty = false;  // some env may hold steps_beyond_terminated = Some(_)
     int vec = 0, block = 0, pdl = 1;
@@ -227,6 +232,7 @@ BatchArgs base_args(const gymrs_env *e)
     a.rk = philox_round_keys(e->seed);
     a.epoch = e->step_count + 1;
     a.epoch_dev = e->epoch_mem;
+    a.epoch_slots = e->epoch_slots;
     a.epoch_from_dev = e->device_counted ? 1 : 0;
     a.err = e->err_dev;
     a.chain_flags = e->chain_mem + 1;
@@ -251,6 +257,8 @@ BatchArgs slice_args(const gymrs_env *e, uint64_t begin, uint64_t count)
     return a;
 }
 
+int default_step_block(int kind) { return kind == GYMRS_PENDULUM ? 256 : 128; }
+
 LaunchOpts make_opts(const gymrs_env *e, uint32_t step_flags)
 {
     LaunchOpts o = {};
@@ -266,7 +274,7 @@ LaunchOpts make_opts(const gymrs_env *e, uint32_t step_flags)
     // L2-resident launches for CartPole and MountainCar; Pendulum is 1 % faster at 256
     // (profiles/r01_sweeps.md).  The persistent kernel (vec = 8) has its own fixed geometry.
     o.block = e->block;
-    if (o.block == 0 && o.vec != 8) o.block = e->kind == GYMRS_PENDULUM ? 256 : 128;
+    if (o.block == 0 && o.vec != 8) o.block = default_step_block(e->kind);
     return o;
 }
 
@@ -308,8 +316,40 @@ int drain_host(gymrs_env *e)
     return GYMRS_OK;
 }
 
-// host-counted launches on a device-counted handle (the sliced host step) publish the new count
-__global__ void set_step_count_kernel(uint64_t *epoch_mem, uint64_t count) { epoch_mem[0] = count; }
+// every per-CTA copy of the step count := count (hand-over at first capture, host steps,
+// checkpoint load) ...
+__global__ void fill_step_count_kernel(uint64_t *epoch_mem, uint64_t slots, uint64_t count)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < slots) epoch_mem[4 + i] = count;
+}
+// ... or := copy 0, which every launch advances (CTA 0 always exists)
+__global__ void spread_step_count_kernel(uint64_t *epoch_mem, uint64_t slots)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t count = epoch_mem[4];
+    if (i >= 1 && i < slots) epoch_mem[4 + i] = count;
+}
+
+cudaError_t fill_step_count(gymrs_env *e, uint64_t count, cudaStream_t s)
+{
+    fill_step_count_kernel<<<(unsigned)((e->epoch_slots + 255) / 256), 256, 0, s>>>(e->epoch_mem, e->epoch_slots, count);
+    return cudaGetLastError();
+}
+
+cudaError_t spread_step_count(gymrs_env *e, cudaStream_t s)
+{
+    spread_step_count_kernel<<<(unsigned)((e->epoch_slots + 255) / 256), 256, 0, s>>>(e->epoch_mem, e->epoch_slots);
+    return cudaGetLastError();
+}
+
+// CTAs of a step launch in the library's default geometry (4 envs per thread): the copies a
+// device-counted launch may rely on without refreshing them
+uint64_t canonical_ctas(const gymrs_env *e)
+{
+    const uint64_t per_cta = 4ull * (uint64_t)default_step_block(e->kind);
+    return (e->n + per_cta - 1) / per_cta;
+}
 
 // Is the handle's stream being captured into a CUDA graph?  (The legacy default stream cannot be.)
 bool capturing(const gymrs_env *e)
@@ -342,12 +382,11 @@ int begin_device_counting(gymrs_env *e)
     if (e->device_counted) return GYMRS_OK;
     if (e->host_inflight) return fail(GYMRS_ERR_UNSUPPORTED, "a host step is in flight: gymrs_host_wait before capturing");
     uint64_t *stage = reinterpret_cast<uint64_t *>(e->err_host + 8);
-    stage[0] = e->step_count;
-    stage[1] = 0; // CTA arrival counter
-    stage[2] = e->seed;
+    stage[0] = e->seed;
     cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
     CU(cudaThreadExchangeStreamCaptureMode(&mode));
-    cudaError_t ce = cudaMemcpyAsync(e->epoch_mem, stage, 3 * sizeof(uint64_t), cudaMemcpyHostToDevice, e->copy_streams[0]);
+    cudaError_t ce = cudaMemcpyAsync(e->epoch_mem + 2, stage, sizeof(uint64_t), cudaMemcpyHostToDevice, e->copy_streams[0]);
+    if (ce == cudaSuccess) ce = fill_step_count(e, e->step_count, e->copy_streams[0]);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->copy_streams[0]);
     cudaThreadExchangeStreamCaptureMode(&mode);
     if (ce != cudaSuccess) return cuda_fail(ce, "handing the step counter over to the device");
@@ -359,7 +398,7 @@ int begin_device_counting(gymrs_env *e)
 int refresh_step_count(gymrs_env *e)
 {
     if (!e->device_counted) return GYMRS_OK;
-    CU(cudaMemcpyAsync(&e->step_count, e->epoch_mem, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(&e->step_count, e->epoch_mem + 4, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return GYMRS_OK;
 }
@@ -428,8 +467,9 @@ int alloc_env(gymrs_env *e)
     const size_t chain_words = (size_t)((n + 31) / 32) + 2; // V = 1, 32-thread CTAs is the finest geometry
     CU(cudaMalloc(&e->chain_mem, chain_words * sizeof(uint32_t)));
     CU(cudaMemsetAsync(e->chain_mem, 0, chain_words * sizeof(uint32_t), e->stream));
-    CU(cudaMalloc(&e->epoch_mem, 4 * sizeof(uint64_t)));
-    CU(cudaMemsetAsync(e->epoch_mem, 0, 4 * sizeof(uint64_t), e->stream));
+    e->epoch_slots = (n + 31) / 32 + 1; // one copy per CTA of the finest geometry (V = 1, 32 threads)
+    CU(cudaMalloc(&e->epoch_mem, (4 + e->epoch_slots) * sizeof(uint64_t)));
+    CU(cudaMemsetAsync(e->epoch_mem, 0, (4 + e->epoch_slots) * sizeof(uint64_t), e->stream));
     CU(cudaHostAlloc(&e->err_host, 16 * sizeof(uint32_t), cudaHostAllocMapped)); // [8..13]: staging, begin_device_counting
     std::memset(e->err_host, 0, 16 * sizeof(uint32_t));
     CU(cudaHostGetDevicePointer(&e->err_dev, e->err_host, 0));
@@ -579,10 +619,13 @@ int gymrs_clone(const gymrs_env *src, gymrs_env **out)
     cp(e->truncated, src->truncated, e->ld);
     cp(e->sbt, src->sbt, sizeof(int32_t) * e->ld);
     cp(e->elapsed, src->elapsed, sizeof(uint32_t) * e->ld);
-    cp(e->epoch_mem, src->epoch_mem, sizeof(uint64_t));         // the count, not the arrival counter
     cp(e->epoch_mem + 2, src->epoch_mem + 2, sizeof(uint64_t)); // the seed
-    if (ce == cudaSuccess && src->device_counted)
-        ce = cudaMemcpyAsync(&e->step_count, e->epoch_mem, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess && src->device_counted) {
+        // copy 0 of the source is always current: take the count from it and fill every copy
+        ce = cudaMemcpyAsync(&e->step_count, src->epoch_mem + 4, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce == cudaSuccess) ce = fill_step_count(e, e->step_count, e->stream);
+    }
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     if (ce != cudaSuccess) {
         free_env(e);
@@ -677,7 +720,7 @@ int gymrs_reset(gymrs_env *e, const uint64_t *seed, const float *low, const floa
     fold_params(e);
     if (ce != cudaSuccess) return cuda_fail(ce, "reset launch");
     if (!mask) { // a full reset restarts the handle's auto-reset stream
-        e->seed = s; // on a device-counted handle the reset kernel also zeroes the device counter and records the seed
+        e->seed = s; // on a device-counted handle the reset kernel also zeroes the device counters and records the seed
         e->step_count = 0;
         e->sbt_dirty = false;
     }
@@ -696,6 +739,8 @@ int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
     LaunchOpts o = make_opts(e, step_flags);
     // device-counted steps read the counter after a grid-wide dependency: no chained launches
     if (e->device_counted && o.pdl == 2) o.pdl = 1;
+    const bool odd_grid = e->device_counted && device_counted_ctas(a, o, false) != canonical_ctas(e);
+    if (odd_grid) CU(spread_step_count(e, e->stream));
     // Chained launch: this step may skip the grid-wide dependency on the previous launch when the
     // handle's per-CTA flags describe its current state for exactly this CTA -> env mapping.
     const int fe = (int)flag_envs(a, o);
@@ -704,6 +749,7 @@ int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
     a.publish = (o.pdl == 2) ? 1 : 0;
     e->chain_ok = false;
     CU(do_step(e, a, o, e->stream, false));
+    if (odd_grid) CU(spread_step_count(e, e->stream));
     e->chain_ok = a.publish != 0; // a pdl == 2 step publishes its flags, chained or not
     e->chain_flag_envs = fe;
     e->chain_stream = e->stream;
@@ -790,10 +836,7 @@ int gymrs_step_host_async(gymrs_env *e, const void *actions, uint32_t step_flags
     }
     CU(cudaEventRecord(e->hev[HostEv::host_done(par)], d2h));
     after_step(e, step_flags, 1);
-    if (e->device_counted) {
-        set_step_count_kernel<<<1, 1, 0, cs>>>(e->epoch_mem, e->step_count);
-        CU(cudaGetLastError());
-    }
+    if (e->device_counted) CU(fill_step_count(e, e->step_count, cs)); // the slices were host-counted
     e->host_inflight = true;
     e->host_seq = tk + 1;
     if (ticket) *ticket = tk;
@@ -853,7 +896,10 @@ int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t 
     // measured (profiles/r01_sweeps.md): CartPole 209 G env-steps/s at 128 threads vs 200 G at 256;
     // MountainCar 287 vs 305, Pendulum 236 vs 246
     if (e->block == 0) o.block = e->kind == GYMRS_CARTPOLE ? 128 : 256;
+    const bool odd_grid = e->device_counted && device_counted_ctas(a, o, true) != canonical_ctas(e);
+    if (odd_grid) CU(spread_step_count(e, e->stream));
     CU(do_step(e, a, o, e->stream, true));
+    if (odd_grid) CU(spread_step_count(e, e->stream));
     after_step(e, step_flags, n_steps);
     return GYMRS_OK;
 }
@@ -1076,8 +1122,8 @@ int gymrs_checkpoint_load(gymrs_env *e, const void *buf, size_t bytes)
     CU(cudaMemcpyAsync(e->truncated, in + l.truncated, n, cudaMemcpyHostToDevice, s));
     if (l.sbt) CU(cudaMemcpyAsync(e->sbt, in + l.sbt, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
     if (l.elapsed) CU(cudaMemcpyAsync(e->elapsed, in + l.elapsed, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(e->epoch_mem, &h.step_count, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(e->epoch_mem + 2, &h.seed, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CU(fill_step_count(e, h.step_count, s));
     CU(cudaStreamSynchronize(s));
     e->global_off = h.global_off;
     e->seed = h.seed;

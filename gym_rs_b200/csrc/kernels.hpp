@@ -26,13 +26,14 @@ struct BatchArgs {
     uint64_t global_off; // global id of env 0
     PhiloxKeys rk;       // Philox round keys of the handle's seed (philox_round_keys)
     uint64_t epoch;      // Philox counter high half for auto-resets in this step (rollout: first step)
-    // Device copy of the handle's step counter: epoch_dev[0] = steps since the last full reset,
-    // low word of epoch_dev[1] = CTA arrival counter, epoch_dev[2] = seed of that reset.
-    // epoch_from_dev == 0: the kernel uses `epoch` (counted on the host) and never touches the
-    // device copy; == 1: the kernel reads the count itself after its dependency wait and the last
-    // CTA to finish advances it -- the form a CUDA graph needs, where kernel arguments are frozen
-    // at capture but every replay is a new step.
+    // Device copies of the handle's step counter: epoch_dev[2] = seed of the last full reset,
+    // epoch_dev[4 + b] = steps since that reset as seen by CTA b (epoch_slots copies, one per CTA
+    // of the finest launch geometry).  epoch_from_dev == 0: the kernel uses `epoch` (counted on the
+    // host) and never touches them; == 1: each CTA reads and advances its own copy after the
+    // dependency wait -- the form a CUDA graph needs, where kernel arguments are frozen at capture
+    // but every replay is a new step.
     uint64_t *epoch_dev;
+    uint64_t epoch_slots;
     int epoch_from_dev;
     uint32_t *err;       // device-visible words: [0] invalid-action flag, [1..2] one offending global id,
                          // [3] chained-dependency timeout flag, [4] the offending action's bits,
@@ -112,6 +113,14 @@ inline bool use_l2_prefetch(const LaunchOpts &o)
         return e && std::string(e) == "0";
     }();
     return o.pdl == 1 && !disabled;
+}
+
+// CTAs of a device-counted launch (they use the 128-bit path or the scalar one, dispatch_vec)
+inline uint64_t device_counted_ctas(const BatchArgs &a, const LaunchOpts &o, bool rollout)
+{
+    const uint64_t v = pick_vec(a, o.vec, rollout) == 4 ? 4 : 1;
+    const uint64_t per_cta = v * (uint64_t)pick_block(o);
+    return (a.n + per_cta - 1) / per_cta;
 }
 
 // env instances covered by one chained-launch progress flag for this launch

@@ -133,36 +133,37 @@ __device__ __forceinline__ void report_invalid(uint32_t *err, uint64_t gid, uint
 
 // ---- step counter on the device (BatchArgs::epoch_dev) ----------------------------
 // DEVC = false (every eager launch of a handle that was never captured): the epoch is the kernel
-// argument the host counted; the device copy is not touched and the code below compiles away.
+// argument the host counted; the device copies are not touched and the code below compiles away.
 // DEVC = true (the handle's steps have been captured into a CUDA graph, where kernel arguments
-// are frozen but every replay is a new step): the launch reads the count once the previous grid
-// is done ...
+// are frozen but every replay is a new step): the count lives in HBM, one private copy per CTA
+// (epoch_dev[4 + blockIdx.x]).  Every thread loads its CTA's copy right after the dependency wait
+// (one request per warp, 2048 different lines per grid) and nothing uses the value before the
+// reset loop, so the load rides along with the row loads; thread 0 advances the copy behind one
+// barrier at the very end, when every warp of the CTA has its value.  Only CTA b ever touches
+// copy b within a grid and the next device-counted launch reads it behind a grid-wide dependency
+// (such launches never chain), so there is no atomic and no hot spot.  Measured alternatives
+// (profiles/r01_sweeps.md): one shared counter + an atomicAdd per CTA, per-CTA copies handed
+// through shared memory at the top or behind the row loads, a lazy read inside the reset loop.
+// The host keeps the copies of CTAs a launch geometry does not cover up to date (capi.cu,
+// spread_step_count).
 template <bool DEVC>
 __device__ __forceinline__ uint64_t first_epoch(const BatchArgs &a)
 {
-    if constexpr (!DEVC) return a.epoch;
-    // epoch_dev[2] is the seed of the handle's last full reset.  The Philox keys of this launch were
-    // frozen when it was captured; if the handle has been re-seeded since, the replay would draw
-    // from the old stream -- raise the sticky error word (gymrs_sync reports it) instead.
-    if (blockIdx.x == 0 && threadIdx.x == 0 &&
-        __ldcg(a.epoch_dev + 2) != ((uint64_t)a.rk.k[0][0] | ((uint64_t)a.rk.k[0][1] << 32)))
-        *reinterpret_cast<volatile uint32_t *>(a.err + 5) = 1u;
-    return __ldcg(a.epoch_dev) + 1u;
+    if constexpr (DEVC) return __ldcg(a.epoch_dev + 4 + blockIdx.x) + 1u;
+    else return a.epoch;
 }
-// ... and the last CTA of the grid to get here advances it.  Every thread of the CTA has read the
-// counter before the barrier, and the next device-counted launch reads it only after this grid
-// has completed (it never skips the grid-wide dependency), so the plain store is race-free.
 template <bool DEVC>
-__device__ __forceinline__ void finish_epoch(const BatchArgs &a, uint64_t first, uint32_t n_steps)
+__device__ __forceinline__ void advance_epoch(const BatchArgs &a, uint64_t first, uint32_t n_steps)
 {
     if constexpr (DEVC) {
-        __syncthreads();
+        __syncthreads(); // every warp of the CTA has read the copy
         if (threadIdx.x == 0) {
-            uint32_t *arrived = reinterpret_cast<uint32_t *>(a.epoch_dev + 1);
-            if (atomicAdd(arrived, 1u) == gridDim.x - 1) {
-                *arrived = 0u;
-                *a.epoch_dev = first - 1u + n_steps;
-            }
+            a.epoch_dev[4 + blockIdx.x] = first - 1u + n_steps;
+            // epoch_dev[2] is the seed of the handle's last full reset.  The Philox keys of this
+            // launch were frozen when it was captured; if the handle has been re-seeded since, the
+            // replay drew from the old stream -- raise the sticky error word (gymrs_sync reports it).
+            if (blockIdx.x == 0 && __ldcg(a.epoch_dev + 2) != ((uint64_t)a.rk.k[0][0] | ((uint64_t)a.rk.k[0][1] << 32)))
+                *reinterpret_cast<volatile uint32_t *>(a.err + 5) = 1u;
         }
     }
 }
@@ -345,7 +346,7 @@ step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Bat
         if (full) step_body<E, V, AR, SBT, TL, true>(p, a, i0, nvalid, act, epoch);
         else step_body<E, V, AR, SBT, TL, false>(p, a, i0, nvalid, act, epoch);
     }
-    finish_epoch<DEVC>(a, epoch, 1u);
+    advance_epoch<DEVC>(a, epoch, 1u);
 
     // publish "this CTA's envs are at step chain_seq" for the next chained launch.  The barrier
     // orders every thread's stores before thread 0's release (cumulativity), so one release store
@@ -630,7 +631,7 @@ rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ 
     const uint64_t epoch = first_epoch<DEVC>(a);
     if (i0 + V <= a.n) rollout_body<E, V, AR, SBT, TL, true>(p, a, i0, V, epoch);
     else if (i0 < a.n) rollout_body<E, V, AR, SBT, TL, false>(p, a, i0, (int)(a.n - i0), epoch);
-    finish_epoch<DEVC>(a, epoch, a.n_steps);
+    advance_epoch<DEVC>(a, epoch, a.n_steps);
 }
 
 // ---- reset ----------------------------------------------------------------------
@@ -641,9 +642,9 @@ reset_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Ba
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    if (i == 0 && !mask && a.epoch_from_dev) { // a full reset restarts the device step counter under this seed
-        a.epoch_dev[0] = 0;
-        a.epoch_dev[2] = (uint64_t)a.rk.k[0][0] | ((uint64_t)a.rk.k[0][1] << 32);
+    if (!mask && a.epoch_from_dev) { // a full reset restarts the device step counters under this seed
+        for (uint64_t c = i; c < a.epoch_slots; c += a.n) a.epoch_dev[4 + c] = 0;
+        if (i == 0) a.epoch_dev[2] = (uint64_t)a.rk.k[0][0] | ((uint64_t)a.rk.k[0][1] << 32);
     }
     if (mask && !mask[i]) return;
     float s[E::SD], o[E::OD];

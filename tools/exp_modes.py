@@ -81,5 +81,22 @@ for pool_name, count in (("ring", RING), ("resident", 1)):
                 us = time_region(replay) * STEPS / (STEPS // span * span)
                 print(f"{env_name} {pool_name:8s} graph of {span:3d} steps:   {us:6.2f} us/step", flush=True)
                 del graph
+            # the handles are device-counted now: the same eager loop runs the DEVC kernel variants
+            print(f"{env_name} {pool_name:8s} eager pdl=1, device-counted kernels: {time_region(eager):6.2f} us/step", flush=True)
+            for e, _ in envs:
+                e.set_launch_config(0, 0, 0)
+            print(f"{env_name} {pool_name:8s} eager pdl=0, device-counted kernels: {time_region(eager):6.2f} us/step", flush=True)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                for i in range(len(sched)):
+                    _capi.check(L.gymrs_step(sched[i][0], sched[i][1], 1))
+
+            def replay0():
+                with torch.cuda.stream(stream):
+                    for _ in range(STEPS // len(sched)):
+                        graph.replay()
+            replay0()
+            print(f"{env_name} {pool_name:8s} graph captured with pdl=0:            {time_region(replay0) * STEPS / (STEPS // len(sched) * len(sched)):6.2f} us/step", flush=True)
+            del graph
         for e, _ in envs:
             e.close()
