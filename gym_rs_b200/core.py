@@ -140,6 +140,9 @@ class Env(EnvProperties):
         self._t_truncated = _as_tensor(b.truncated, (n,), "|u1", None, dev)
         self._t_sbt = (_as_tensor(b.steps_beyond_terminated, (n,), "<i4", None, dev)
                        if b.steps_beyond_terminated else None)
+        self._batched_result = ActionReward(self._t_obs, self._t_reward, self._t_done, self._t_truncated,
+                                            self.INFO_ON_STEP)
+        self._checked_action = None
 
     def _refresh_spaces(self):
         n = C.c_uint64()
@@ -250,9 +253,16 @@ class Env(EnvProperties):
             _capi.check(rc)
             return ActionReward(self.OBSERVATION(*[float(v) for v in obs[:, 0]]), float(rew[0]),
                                 bool(dn[0]), bool(tr[0]), self.INFO_ON_STEP)
-        self._check_actions(action)
-        _capi.check(self._L.gymrs_step(self._h, C.c_void_p(action.data_ptr()), flags))
-        return ActionReward(self._t_obs, self._t_reward, self._t_done, self._t_truncated, self.INFO_ON_STEP)
+        # A 1 M-env step is ~6 us of GPU time, so the host side of this call matters: the checks
+        # are skipped for a tensor object that already passed them, and the result record (views of
+        # the handle's fixed buffers) is built once.
+        if action is not self._checked_action:
+            self._check_actions(action)
+            self._checked_action = action
+        rc = self._L.gymrs_step(self._h, action.data_ptr(), flags)
+        if rc:
+            _capi.check(rc)
+        return self._batched_result
 
     def _check_actions(self, action, steps: int = 1):
         import torch
