@@ -28,8 +28,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's banner / debug lines (NCCL_DEBUG set on the box) go to stderr
+# stdout carries exactly one JSON line.  NCCL prints its version banner with a plain printf when
+# NCCL_DEBUG is set on the box, so file descriptor 1 is pointed at stderr for the whole run and the
+# JSON line is written to a private duplicate of the original stdout (emit).
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def quiet_stdout() -> None:
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 N_ENVS = 1 << 20
 RING = 16
@@ -209,7 +225,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------
@@ -500,7 +516,7 @@ def run_b200(args):
             "all_ms_per_step": [t / K for t in times][:40],
             "ms_per_step_min_max": [min(times) / K, max(times) / K],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     for e, _ in ring:
         e.close()
     if world > 1:
@@ -509,6 +525,7 @@ def run_b200(args):
 
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
