@@ -773,8 +773,9 @@ int gymrs_step_host_async(gymrs_env *e, const void *actions, uint32_t step_flags
     if (int rc_ = refuse_in_capture(e, "gymrs_step_host")) return rc_;
     ON_DEVICE(e->device);
     if (e->device_counted && !e->host_inflight) {
-        // host steps are sliced into several launches that must share one epoch: count on the
-        // host for the duration (the kernels keep recording the count on the device)
+        // host steps are sliced into several launches that must share one epoch: they are
+        // host-counted (from the device's current count), and the new count is written back to
+        // every device copy after the slices (fill_step_count below)
         if (int rc_ = refresh_step_count(e)) return rc_;
     }
     const uint64_t n = e->n;

@@ -49,6 +49,7 @@ def test_struct_sizes_match_the_header():
     assert C.sizeof(_capi.MountainCarParams) == 7 * 8 + 8
     assert C.sizeof(_capi.PendulumParams) == 6 * 8 + 8
     assert C.sizeof(_capi.Buffers) == 16 + 8 + 7 * 8
+    assert C.sizeof(_capi.CheckpointInfo) == 4 + 4 + 5 * 8
 
 
 def test_default_params_are_the_reference_constants():
