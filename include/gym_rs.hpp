@@ -10,6 +10,7 @@
 //   gym_rs::utils::seeding::rand_random         src/utils/seeding.rs:21-26
 //   gym_rs::envs::classical_control::cartpole::CartPoleEnv       cartpole.rs:51-87, :389-516
 //   gym_rs::envs::classical_control::mountain_car::MountainCarEnv mountain_car.rs:46-84, :391-501
+//   gym_rs::batched::BatchedEnv                 N instances per handle (no counterpart: F9 in SURVEY.md)
 //
 // The reference panics on an invalid action (assert!, cartpole.rs:402-406); here that is a
 // gym_rs::Panic exception carrying the reference's message text.
@@ -231,5 +232,102 @@ class MountainCarEnv : public core::EnvBase<MountainCarEnv, MountainCarObservati
 };
 } // namespace mountain_car
 } // namespace envs::classical_control
+
+// N env instances per handle: the shape the GPU path is built for.  ActionReward carries a scalar
+// reward / done (core.rs:94-106), so the batched surface hands out struct-of-arrays host vectors
+// instead (observation[k * num_envs + i] is field k of env i).  Same role as rust/src/batched.rs.
+namespace batched {
+enum class Kind { CartPole = GYMRS_CARTPOLE, MountainCar = GYMRS_MOUNTAIN_CAR, Pendulum = GYMRS_PENDULUM };
+
+struct BatchStep {
+    const std::vector<float> &observation;
+    const std::vector<float> &reward;
+    const std::vector<uint8_t> &done;
+    const std::vector<uint8_t> &truncated;
+};
+
+class BatchedEnv {
+  public:
+    // global_env_offset keys the reset RNG, so shards of one logical batch on several GPUs give the
+    // same per-env results as a single handle
+    BatchedEnv(Kind kind, size_t num_envs, int device = 0, uint64_t global_env_offset = 0, bool time_limit = false)
+        : kind_(kind), n_(num_envs)
+    {
+        check(gymrs_create((int)kind, num_envs, device, global_env_offset, nullptr,
+                           time_limit ? GYMRS_FLAG_TIME_LIMIT : 0u, &handle_));
+        gymrs_buffers b;
+        check(gymrs_get_buffers(handle_, &b));
+        obs_dim_ = b.obs_dim;
+        obs_.resize(obs_dim_ * n_);
+        reward_.resize(n_);
+        done_.resize(n_);
+        truncated_.resize(n_);
+    }
+    BatchedEnv(const BatchedEnv &) = delete;
+    BatchedEnv &operator=(const BatchedEnv &) = delete;
+    ~BatchedEnv()
+    {
+        if (handle_) gymrs_destroy(handle_);
+    }
+
+    uint64_t reset(std::optional<uint64_t> seed)
+    {
+        uint64_t s = seed ? *seed : 0, used = 0;
+        check(gymrs_reset(handle_, seed ? &s : nullptr, nullptr, nullptr, nullptr, &used));
+        return used;
+    }
+
+    // Discrete envs.  Panics like the reference on an action outside the action space.
+    BatchStep step(const std::vector<size_t> &actions, bool autoreset)
+    {
+        if (actions.size() != n_) throw Panic("one action per env instance");
+        actions_.resize(n_);
+        for (size_t i = 0; i < n_; ++i) actions_[i] = actions[i] > 0x7fffffffu ? 0x7fffffff : (int32_t)actions[i];
+        return run(actions_.data(), autoreset, [&](uint64_t bad) {
+            const size_t a = actions[bad % n_];
+            return std::to_string(a) + (kind_ == Kind::MountainCar ? " (usize) invalid" : " usize invalid");
+        });
+    }
+    // Pendulum: continuous torque per env
+    BatchStep step(const std::vector<float> &actions, bool autoreset)
+    {
+        if (actions.size() != n_) throw Panic("one action per env instance");
+        return run(actions.data(), autoreset, [](uint64_t) { return std::string("invalid action"); });
+    }
+
+    // the whole handle as one blob; restore() resumes bit-identically (checkpoint / resume)
+    std::vector<unsigned char> checkpoint()
+    {
+        size_t bytes = 0;
+        check(gymrs_checkpoint_size(handle_, &bytes));
+        std::vector<unsigned char> blob(bytes);
+        check(gymrs_checkpoint_save(handle_, blob.data(), bytes));
+        return blob;
+    }
+    void restore(const std::vector<unsigned char> &blob) { check(gymrs_checkpoint_load(handle_, blob.data(), blob.size())); }
+
+    size_t num_envs() const { return n_; }
+    size_t obs_dim() const { return obs_dim_; }
+    gymrs_env *handle() { return handle_; } // for callers that keep actions / results on the device
+
+  private:
+    template <class Msg> BatchStep run(const void *actions, bool autoreset, Msg message)
+    {
+        check(gymrs_step_host(handle_, actions, autoreset ? GYMRS_STEP_AUTORESET : 0u, obs_.data(), reward_.data(),
+                              done_.data(), truncated_.data()));
+        uint64_t bad = 0;
+        const int rc = gymrs_sync(handle_, &bad);
+        if (rc == GYMRS_ERR_INVALID_ACTION) throw Panic(message(bad)); // assert!, cartpole.rs:402-406
+        check(rc);
+        return {obs_, reward_, done_, truncated_};
+    }
+    Kind kind_;
+    size_t n_, obs_dim_ = 0;
+    gymrs_env *handle_ = nullptr;
+    std::vector<int32_t> actions_;
+    std::vector<float> obs_, reward_;
+    std::vector<uint8_t> done_, truncated_;
+};
+} // namespace batched
 
 } // namespace gym_rs

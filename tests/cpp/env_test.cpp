@@ -128,6 +128,56 @@ static void mountain_car_plumbing()
     EXPECT(threw);
 }
 
+static void batched_plumbing()
+{
+    using gym_rs::batched::BatchedEnv;
+    using gym_rs::batched::Kind;
+    const size_t n = 5000;
+    BatchedEnv env(Kind::CartPole, n, 0, 100);
+    EXPECT(env.reset(7) == 7 && env.obs_dim() == 4);
+    std::vector<size_t> act(n);
+    std::mt19937 rng(3);
+    // sampled envs against their own scalar oracle object, resynchronised each step
+    std::vector<float> before = env.step(std::vector<size_t>(n, 1), false).observation; // a copy: the views are reused
+    for (int t = 0; t < 20; ++t) {
+        for (auto &a : act) a = rng() % 2;
+        auto st = env.step(act, false);
+        for (size_t i = 0; i < n; i += 97) {
+            orc_cartpole_env o;
+            orc_cartpole_new(&o);
+            for (int k = 0; k < 4; ++k) o.state[k] = before[k * n + i];
+            double r; int d, tr;
+            orc_cartpole_step(&o, act[i], &r, &d, &tr);
+            for (int k = 0; k < 4; ++k) EXPECT(close6(st.observation[k * n + i], o.state[k]));
+            const bool in_band = std::fabs(std::fabs(o.state[0]) - 2.4) < 1e-6 ||
+                                 std::fabs(std::fabs(o.state[2]) - 0.20943951023931953) < 1e-6;
+            EXPECT(in_band || (st.done[i] != 0) == (d != 0));
+        }
+        before = st.observation;
+    }
+    // auto-reset keeps every env inside the live region; checkpoint / restore retraces the same step
+    for (int t = 0; t < 50; ++t) {
+        for (auto &a : act) a = rng() % 2;
+        env.step(act, true);
+    }
+    auto blob = env.checkpoint();
+    std::vector<float> first = env.step(act, true).observation;
+    env.step(act, true);
+    env.restore(blob);
+    EXPECT(env.step(act, true).observation == first);
+    for (size_t i = 0; i < n; ++i) EXPECT(std::fabs(first[i]) <= 2.4f + 1e-3f);
+    // an invalid action anywhere in the batch panics with the reference's message
+    act[1234] = 2;
+    bool threw = false;
+    try { env.step(act, true); } catch (const Panic &e) { threw = std::string(e.what()) == "2 usize invalid"; }
+    EXPECT(threw);
+    // Pendulum takes float torques
+    BatchedEnv pd(Kind::Pendulum, 1000);
+    pd.reset(1);
+    auto ps = pd.step(std::vector<float>(1000, 0.5f), true);
+    EXPECT(pd.obs_dim() == 3 && ps.reward[0] <= 0.0f && ps.done[0] == 0);
+}
+
 int main()
 {
     reference_unit_tests();
@@ -141,6 +191,7 @@ int main()
     }
     cartpole_plumbing();
     mountain_car_plumbing();
+    batched_plumbing();
     std::printf("env_test: failures=%d\n", failures);
     return failures ? 1 : 0;
 }
