@@ -251,7 +251,7 @@ class BatchedEnv {
     // global_env_offset keys the reset RNG, so shards of one logical batch on several GPUs give the
     // same per-env results as a single handle
     BatchedEnv(Kind kind, size_t num_envs, int device = 0, uint64_t global_env_offset = 0, bool time_limit = false)
-        : kind_(kind), n_(num_envs)
+        : kind_(kind), n_(num_envs), global_off_(global_env_offset)
     {
         check(gymrs_create((int)kind, num_envs, device, global_env_offset, nullptr,
                            time_limit ? GYMRS_FLAG_TIME_LIMIT : 0u, &handle_));
@@ -284,7 +284,7 @@ class BatchedEnv {
         actions_.resize(n_);
         for (size_t i = 0; i < n_; ++i) actions_[i] = actions[i] > 0x7fffffffu ? 0x7fffffff : (int32_t)actions[i];
         return run(actions_.data(), autoreset, [&](uint64_t bad) {
-            const size_t a = actions[bad % n_];
+            const size_t a = actions[(bad - global_off_) % n_]; // gymrs_sync reports the GLOBAL env id
             return std::to_string(a) + (kind_ == Kind::MountainCar ? " (usize) invalid" : " usize invalid");
         });
     }
@@ -323,6 +323,7 @@ class BatchedEnv {
     }
     Kind kind_;
     size_t n_, obs_dim_ = 0;
+    uint64_t global_off_ = 0;
     gymrs_env *handle_ = nullptr;
     std::vector<int32_t> actions_;
     std::vector<float> obs_, reward_;

@@ -23,6 +23,7 @@ pub struct BatchStep<'a> {
 pub struct BatchedEnv {
     handle: *mut ffi::gymrs_env,
     num_envs: usize,
+    global_env_offset: u64,
     obs_dim: usize,
     actions: Vec<i32>,
     obs: Vec<f32>,
@@ -48,6 +49,7 @@ impl BatchedEnv {
         Self {
             handle,
             num_envs,
+            global_env_offset,
             obs_dim,
             actions: vec![0; num_envs],
             obs: vec![0.0; obs_dim * num_envs],
@@ -78,7 +80,8 @@ impl BatchedEnv {
             let mut bad = 0u64;
             let rc = ffi::gymrs_sync(self.handle, &mut bad);
             if rc == ffi::GYMRS_ERR_INVALID_ACTION {
-                panic!("{} usize invalid", actions[(bad as usize) % self.num_envs]);
+                // gymrs_sync reports the GLOBAL env id
+                panic!("{} usize invalid", actions[((bad - self.global_env_offset) as usize) % self.num_envs]);
             }
             ffi::check(rc);
         }
