@@ -22,7 +22,17 @@ bench-reference:  ## the reference-equivalent scalar CPU loop
 golden:           ## regenerate tests/golden/step_vectors.json (mpmath)
 	$(PY) tests/golden/make_golden.py
 
-clean:
-	rm -rf gym_rs_b200/libgymrs_b200.so gym_rs_b200/csrc/build oracle/libgymrs_oracle.so tests/cpp/env_test
+gpu-check:        ## on a GPU box: parity tests, smoke, one bench line per env (set GYMRS_CHECK_ENVS)
+	bash tools/gpu_check.sh
 
-.PHONY: build test test-gpu smoke bench bench-reference golden clean
+profile:          ## on a GPU box: the ncu passes behind profiles/ (then: python profiles/summarize.py r01)
+	bash tools/profile_round.sh
+
+sanitize:         ## on a GPU box: compute-sanitizer memcheck / racecheck / initcheck / synccheck
+	bash tools/sanitize_round.sh
+
+clean:
+	rm -rf gym_rs_b200/libgymrs_b200.so gym_rs_b200/csrc/build oracle/libgymrs_oracle.so tests/cpp/env_test \
+	       tests/cuda/curand_check tools/bin
+
+.PHONY: build test test-gpu smoke bench bench-reference golden gpu-check profile sanitize clean
