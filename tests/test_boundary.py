@@ -36,6 +36,13 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert L.gymrs_abi_version() == 1
 
 
+def test_every_entry_point_is_mapped_to_a_reference_item_in_integration_md():
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for name in header_functions():
+        short = name.replace("gymrs_checkpoint", "")  # the checkpoint family is listed as `_save` / `_load` / ...
+        assert name in doc or (name.startswith("gymrs_checkpoint") and "`" + short + "`" in doc), name
+
+
 def test_library_is_compiled_for_sm_100a():
     from gym_rs_b200 import _capi
     _capi.load()
