@@ -13,6 +13,11 @@ pub const GYMRS_PENDULUM: c_int = 2;
 
 pub const GYMRS_OK: c_int = 0;
 pub const GYMRS_ERR_INVALID_ACTION: c_int = 1;
+pub const GYMRS_ERR_BAD_ARG: c_int = 2;
+pub const GYMRS_ERR_CUDA: c_int = 3;
+pub const GYMRS_ERR_NO_DEVICE: c_int = 4;
+pub const GYMRS_ERR_ALLOC: c_int = 5;
+pub const GYMRS_ERR_UNSUPPORTED: c_int = 6;
 
 pub const GYMRS_FLAG_TIME_LIMIT: u32 = 0x1;
 pub const GYMRS_STEP_AUTORESET: u32 = 0x1;
@@ -42,6 +47,19 @@ pub struct gymrs_mountain_car_params {
     pub goal_velocity: f64,
     pub force: f64,
     pub gravity: f64,
+    pub max_episode_steps: i32,
+    pub _pad: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct gymrs_pendulum_params {
+    pub max_speed: f64,
+    pub max_torque: f64,
+    pub dt: f64,
+    pub g: f64,
+    pub m: f64,
+    pub l: f64,
     pub max_episode_steps: i32,
     pub _pad: i32,
 }

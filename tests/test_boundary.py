@@ -43,6 +43,16 @@ def test_every_entry_point_is_mapped_to_a_reference_item_in_integration_md():
         assert name in doc or (name.startswith("gymrs_checkpoint") and "`" + short + "`" in doc), name
 
 
+def test_rust_and_cpp_bindings_declare_or_use_the_same_abi():
+    """The Rust binding cannot be compiled in this image; at least keep its extern block in step
+    with the header, symbol by symbol."""
+    ffi = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    for name in header_functions():
+        assert f"fn {name}(" in ffi, f"{name} missing from rust/src/ffi.rs"
+    for const in ("GYMRS_ERR_UNSUPPORTED: c_int = 6", "GYMRS_STEP_AUTORESET: u32 = 0x1", "GYMRS_FLAG_TIME_LIMIT: u32 = 0x1"):
+        assert const in ffi
+
+
 def test_library_is_compiled_for_sm_100a():
     from gym_rs_b200 import _capi
     _capi.load()
