@@ -62,6 +62,17 @@ WORKLOAD = {
 }
 
 
+def config_of(args, world):
+    """The workload description: the SAME dict in the B200 arm and in the reference arm (what is
+    specific to one arm's method goes into its own `method` key)."""
+    n, env = args.envs, args.env
+    return {"workload": WORKLOAD[env], "envs_per_gpu": n,
+            "l2_policy": f"inputs larger than L2: ring of {args.ring} independent {n}-env batches "
+                         f"({args.ring * FOOTPRINT[env] * n / 1e6:.0f} MB footprint per GPU) stepped round-robin, so every "
+                         "launch touches cold HBM lines",
+            "parallelism": f"env batch sharded over {world} GPU(s) by global env id, no collective on the step path"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -78,6 +89,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--ref-repeats", type=int, default=0,
+                    help="reference arm: timed regions of --steps steps (0 = as many as fit ~15 s of wall time, 5 to 200)")
     ap.add_argument("--streams", type=int, default=2,
                     help="the independent ring slots alternate over this many CUDA streams")
     ap.add_argument("--burn-in", type=int, default=300, help="untimed steps per ring slot before warm-up")
@@ -209,8 +222,22 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
+    import oracle
     steps, warmup = args.steps, args.warmup
-    value, t, cores, sample, sample_envs = cpu_rollout(args.env, args.envs, steps, warmup, budget_s=120.0)
+    kind = {"cartpole": oracle.CARTPOLE, "mountain_car": oracle.MOUNTAIN_CAR, "pendulum": oracle.PENDULUM}[args.env]
+    # first region: also calibrates (and, on a slow host, bounds the sample)
+    value, t, cores, sample, sample_envs = cpu_rollout(args.env, args.envs, steps, warmup, budget_s=20.0)
+    # A region of `steps` steps is short (20 steps of 1 M envs = ~30 ms on 32 cores): thread start-up
+    # and cold caches would dominate a single one, so the region is repeated like the B200 arm's
+    # and the median is reported.
+    # (each call also re-creates the env objects, untimed; the wall budget below counts that)
+    times, w0 = [t], time.perf_counter()
+    while len(times) < (args.ref_repeats or 200) and (args.ref_repeats or len(times) < 5
+                                                      or time.perf_counter() - w0 < 15.0):
+        ti, _ = oracle.bench_rollout(kind, sample_envs, steps, warmup, cores, 0)
+        times.append(ti)
+    t = statistics.median(times)
+    value = sample_envs * steps / t
     line = {
         "impl": "reference",
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
@@ -218,10 +245,12 @@ def run_reference(args):
         "ms_per_step": 1e3 * t / steps * (args.envs / sample_envs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD[args.env],
-                   "note": "C restatement (oracle/) of the reference's scalar Rust step loop; the Rust crate itself "
-                           "cannot be built in this image (no cargo, SDL2 dependency)"},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": config_of(args, args.gpus),
+        "method": {"what": "C restatement (oracle/) of the reference's scalar Rust step loop on the host cores; the Rust "
+                           "crate itself cannot be built in this image (no cargo, SDL2 dependency)",
+                   "repeats": len(times), "region_s_min_median_max": [min(times), t, max(times)]},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": sample + f"; median of {len(times)} regions"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -241,6 +270,47 @@ def make_actions(torch, env, n, device, gen):
         return torch.rand((n,), generator=gen, device=device) * 4.0 - 2.0
     hi = 2 if env == "cartpole" else 3
     return torch.randint(0, hi, (n,), generator=gen, device=device, dtype=torch.int32)
+
+
+def kernel_isolated_us(env):
+    """Duration of ONE isolated launch of the step kernel (ncu, cold cache, serialised) from the
+    committed launch list of this bench command: profiles/kernel_isolated.json."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "kernel_isolated.json"))).get(env)
+    except Exception:
+        return None
+
+
+def pcie_ceiling(torch, dist, device, world, h2d_bytes, d2h_bytes, iters=12):
+    """What plain copies of one step's bytes reach on this box with ALL ranks copying at once:
+    per iteration one H2D copy of h2d_bytes and one D2H copy of d2h_bytes from / to pinned memory
+    on two streams (the engines run concurrently, like the e2e pipeline).  Returns aggregate GB/s."""
+    hin = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    hout = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    din = torch.empty(h2d_bytes, dtype=torch.uint8, device=device)
+    dout = torch.zeros(d2h_bytes, dtype=torch.uint8, device=device)
+    s_in, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+    def run(k):
+        for _ in range(k):
+            with torch.cuda.stream(s_in):
+                din.copy_(hin, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hout.copy_(dout, non_blocking=True)
+        s_in.synchronize()
+        s_out.synchronize()
+
+    run(2)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    run(iters)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return world * (h2d_bytes + d2h_bytes) * iters / dt / 1e9
 
 
 def run_b200(args):
@@ -314,9 +384,13 @@ def run_b200(args):
     run_steps(args.burn_in * len(handles) // ACTION_SETS, handles)
     barrier()
 
-    wall = []
+    sanity = {"regions": 0, "device_ms": 0.0, "host_ms": 0.0}
 
     def timed(k, pool):
+        """EXACTLY k steps between two CUDA events on the main stream, bracketed by a barrier + device
+        synchronize on both sides.  Returns this rank's device time (ms); the max over ranks is taken
+        once at the end, on the whole vector of repeats.  The host clock runs from the first launch
+        to the drained device and excludes the barriers; it is only recorded (timing_sanity)."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         w0 = time.perf_counter()
@@ -325,98 +399,145 @@ def run_b200(args):
         run_steps(k, pool)
         join()
         ev1.record(stream)
+        torch.cuda.synchronize(device)
+        w1 = time.perf_counter()
         barrier()
-        wall.append((time.perf_counter() - w0) * 1e3)
         ms = ev0.elapsed_time(ev1)
-        # the device time must account for the host wall time of the same region (launch until
-        # drained); if it does not, the events were not on the stream the kernels ran on.  Regions
-        # shorter than 1 ms are dominated by the fixed cost of the two barriers and are not judged.
-        assert ms > 0.7 * wall[-1] or wall[-1] < 1.0, (ms, wall[-1])
-        if world > 1:
-            t = torch.tensor([ms], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        sanity["regions"] += 1
+        sanity["device_ms"] += ms
+        sanity["host_ms"] += (w1 - w0) * 1e3
         return ms
+
+    def over_ranks(times):
+        """element-wise max over ranks of a list of per-repeat device times"""
+        if world == 1:
+            return list(times)
+        t = torch.tensor(times, device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
 
     run_steps(max(W, 3), handles)  # warm-up (untimed)
     barrier()
     # the timed region: EXACTLY K steps; repeated so the clock sampler sees sustained load, median reported
-    est = timed(K, handles)
-    # enough repeats for ~0.4 s under load (so that the 5 ms clock sampler sees it) whatever K is,
-    # but no more than ~2 s worth; at the default K that is ~25 repeats
-    repeats = int(min(2000, max(3, 400.0 / max(est, 1e-3))))
+    est = over_ranks([timed(K, handles)])[0]
+    # enough repeats for ~0.4 s under load (so that the 5 ms clock sampler sees it) whatever K is;
+    # every repeat costs two barriers, so multi-rank runs are capped lower.  `est` is the max over
+    # ranks, so every rank computes the same count (the barriers must pair up).
+    repeats = int(min(2000 if world == 1 else 400, max(3, 400.0 / max(est, 1e-3))))
     with ClockSampler(local_rank) as cs:
-        times = [timed(K, handles) for _ in range(repeats)]
+        times = over_ranks([timed(K, handles) for _ in range(repeats)])
     clocks = cs.summary()
     ms = statistics.median(times)
-    # Two more figures on ONE stream, with pipelined launches (pdl = 2: a step waits per CTA on
-    # the same CTA of the handle's previous step; valid here because the actions are pre-generated):
-    #   chained  -- the same cold ring, consecutive launches overlap through the per-CTA flags
-    #   resident -- ONE batch stepped back to back (a true dependency chain, state stays in L2)
-    for e, _ in ring:
-        e.set_stream(stream.cuda_stream)
-        e.set_launch_config(vec=args.vec, block=args.block, pdl=2)
-    run_steps(len(handles), handles)
-    chained = [timed(K, handles) for _ in range(3)]
-    resident = [timed(K, resident_pool) for _ in range(3)]
+
+    def one_stream(pdl, pool, reps=3):
+        for e, _ in ring:
+            e.set_stream(stream.cuda_stream)
+            e.set_launch_config(vec=args.vec, block=args.block, pdl=pdl)
+        run_steps(len(pool), pool)
+        return statistics.median(over_ranks([timed(K, pool) for _ in range(reps)]))
+
+    # Figures on ONE stream (what a caller with a single env group sees):
+    #   default  -- pdl = 1, the library default: every launch waits for the whole previous grid.  Valid
+    #               with a policy kernel in the loop that writes the actions right before the step.
+    #   chained  -- pdl = 2: a step waits per CTA on the same CTA of the handle's previous step; valid
+    #               when the actions are pre-generated (as here)
+    # each on the cold ring (HBM) and on ONE batch stepped back to back (a true dependency chain, L2-resident)
+    saved_streams = streams
+    streams = [stream]
+    default_cold = one_stream(1, handles)
+    default_res = one_stream(1, resident_pool)
+    chained = one_stream(2, handles)
+    resident = one_stream(2, resident_pool)
+    streams = saved_streams
     for e, _ in ring:
         e.sync()  # surfaces any invalid-action / CUDA error from the timed launches
 
     value = world * n * K / (ms * 1e-3)
     peak, peak_src = measured_peak()
     achieved = ALGO_BYTES[env] * n * K / (ms * 1e-3) / 1e9  # per-GPU algorithmic GB/s
-    ms_res = statistics.median(resident)
 
-    # ---- e2e: same metric through gymrs_step_host with pinned HOST buffers ------------------
+    def figure(t_ms, note):
+        return {"value": world * n * K / (t_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": t_ms / K,
+                "frac": ALGO_BYTES[env] * n * K / (t_ms * 1e-3) / 1e9 / peak, "note": note}
+
+    # ---- e2e: same metric through the host-buffer entry points, pinned HOST memory -----------
     e2e = None
     if not args.no_e2e:
         e0 = ring[0][0]
+        e0.set_launch_config(vec=args.vec, block=args.block, pdl=1)
         act_dtype = torch.float32 if env == "pendulum" else torch.int32
-        h_acts = [a.cpu().to(act_dtype).pin_memory() for a in ring[0][1][:2]]
-        # two sets of pinned result buffers: step t's results stream out while step t + 1 is submitted
-        h_out = [(torch.empty((e0.obs_dim, n), dtype=torch.float32).pin_memory(),
-                  torch.empty(n, dtype=torch.float32).pin_memory(),
-                  torch.empty(n, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        S = 2  # action slots and result slots: step t's results stream out while step t + 1 is submitted
+        h_acts = torch.stack([a.cpu().to(act_dtype) for a in ring[0][1][:S]]).pin_memory()
+        h_obs = torch.empty((S, e0.obs_dim, n), dtype=torch.float32).pin_memory()
+        h_rew = torch.empty((S, n), dtype=torch.float32).pin_memory()
+        h_done = torch.empty((S, n), dtype=torch.uint8).pin_memory()
+        acc = [0.0, 0]
 
-        def host_loop(steps):
-            """Every step: actions H2D from pinned memory, step kernel, obs / reward / done D2H into
-            pinned memory.  Returns a checksum read from the delivered results of every step."""
-            tickets, acc = [], 0.0
-            for t in range(steps):
-                if t >= 2:
-                    e0.host_wait(tickets[t - 2])          # results of step t - 2 are on the host now
-                    acc += float(h_out[t % 2][1][0]) + float(h_out[t % 2][0][0, n - 1])
-                o, r, d = h_out[t % 2]
-                tickets.append(e0.step_host_async(h_acts[t % 2], o, r, d, None, autoreset=True))
-            for t in range(max(0, steps - 2), steps):
-                e0.host_wait(tickets[t])
-                acc += float(h_out[t % 2][1][0]) + float(h_out[t % 2][0][0, n - 1])
-            return acc
+        def consume(t, slot):
+            # the device -> host read of the step's result: the consumer touches every delivered slot
+            acc[0] += float(h_rew[slot, 0]) + float(h_obs[slot, 0, n - 1]) + float(h_done[slot, n // 2])
+            acc[1] += 1
+
+        def host_loop(steps, **kw):
+            """gymrs_rollout_host: every step copies its actions in from pinned memory, runs the step
+            kernel and copies observation / reward / done out to pinned memory; `consume` runs once
+            per delivered step."""
+            t0 = time.perf_counter()
+            e0.rollout_host(h_acts, kw.get("obs", h_obs), h_rew, kw.get("done", h_done), None, n_steps=steps,
+                            autoreset=True, on_step=consume, u8_actions=kw.get("u8", False),
+                            packed_done=kw.get("packed", False))
+            return time.perf_counter() - t0
+
+        def max_over_ranks(x):
+            if world == 1:
+                return x
+            t = torch.tensor([x], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
 
         host_loop(4)
         barrier()
-        t0 = time.perf_counter()
-        acc = host_loop(args.e2e_steps)
-        torch.cuda.synchronize(device)
-        dt = time.perf_counter() - t0
+        dt = max_over_ranks(host_loop(args.e2e_steps))
+        assert acc[1] == 4 + args.e2e_steps and acc[0] == acc[0]
+        assert bool(torch.isfinite(h_obs).all()) and float(h_rew.abs().sum()) != 0.0
         # the synchronous call (what a scalar Env::step binding uses), for comparison
+        barrier()
         t1 = time.perf_counter()
         for _ in range(10):
-            e0.step_host(h_acts[0], *h_out[0], None, autoreset=True)
-        dt_sync = (time.perf_counter() - t1) / 10
-        if world > 1:
-            t = torch.tensor([dt], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        assert acc == acc and bool(torch.isfinite(h_out[0][0]).all()) and float(h_out[0][1].abs().sum()) != 0.0
+            e0.step_host(h_acts[0], h_obs[0], h_rew[0], h_done[0], None, autoreset=True)
+        dt_sync = max_over_ranks((time.perf_counter() - t1) / 10)
+        # the PCIe / host-memory ceiling of THIS box for the same bytes, all ranks copying at once
+        h2d_b, d2h_b = 4 * n, D2H_BYTES[env] * n
+        barrier()
+        ceiling = pcie_ceiling(torch, dist, device, world, h2d_b, d2h_b)
+        gbs = world * (h2d_b + d2h_b) * args.e2e_steps / dt / 1e9
         e2e = {"value": world * n * args.e2e_steps / dt, "unit": "env-steps/s",
-               "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": D2H_BYTES[env] * n,
-               "steps": args.e2e_steps,
-               "pcie_gbs": (4 + D2H_BYTES[env]) * n * args.e2e_steps / dt / 1e9,
+               "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+               "steps": args.e2e_steps, "pcie_gbs": gbs,
+               "pcie_ceiling_gbs": ceiling, "frac_of_pcie": gbs / ceiling,
+               "ceiling_how": f"plain cudaMemcpyAsync of the same {h2d_b} B in + {d2h_b} B out per iteration from / to pinned "
+                              f"memory on two streams, all {world} rank(s) at once, measured in this run",
                "host_cpus_bound_to_gpu_numa_node": numa,
                "synchronous_value": world * n / dt_sync,
-               "api": "gymrs_step_host_async + gymrs_host_wait, two pinned buffer sets (actions in; obs, reward, "
-                      "done out, every step); synchronous_value = gymrs_step_host, one step at a time"}
+               "api": "gymrs_rollout_host (the library's pipelined host loop: per step, actions in from a pinned slot; "
+                      "observation, reward, done out to a pinned result slot; a consumer callback per delivered step); "
+                      "synchronous_value = gymrs_step_host, one step at a time"}
+        if env != "pendulum":
+            # compact wire formats (lossless): uint8 actions in, done as bits out
+            h_acts8 = h_acts.to(torch.uint8).pin_memory()
+            h_bits = torch.empty((S, (n + 7) // 8), dtype=torch.uint8).pin_memory()
+            keep = h_acts
+            h_acts = h_acts8
+            host_loop(4, u8=True, packed=True, done=h_bits)
+            barrier()
+            dtc = max_over_ranks(host_loop(args.e2e_steps, u8=True, packed=True, done=h_bits))
+            h_acts = keep
+            cb = n + (D2H_BYTES[env] - 1) * n + (n + 7) // 8
+            e2e["compact"] = {"value": world * n * args.e2e_steps / dtc, "unit": "env-steps/s",
+                              "bytes_per_step": cb, "pcie_gbs": world * cb * args.e2e_steps / dtc / 1e9,
+                              "note": "GYMRS_HOST_U8_ACTIONS | GYMRS_HOST_PACKED_DONE: uint8 actions in, done as bits out "
+                                      "(same information, fewer PCIe bytes); not the headline"}
+        del h_acts, h_obs, h_rew, h_done
 
     # ---- fused rollout (labelled separately; never mixed with the single-step figure) ----------
     rollout = None
@@ -443,11 +564,7 @@ def run_b200(args):
             barrier()
             reps.append(ev0.elapsed_time(ev1))
         e0.sync()
-        rms = statistics.median(reps)
-        if world > 1:
-            t = torch.tensor([rms], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            rms = float(t.item())
+        rms = statistics.median(over_ranks(reps))
         rbytes = ROLLOUT_BYTES[env] + 2 * 4 * e0.state_dim / kr
         wbytes = ROLLOUT_BYTES[env] - 4 + 4 * e0.state_dim / kr  # everything but the action row is a WRITE
         # The rollout is ~85 % writes, and write-only HBM traffic has a lower ceiling than the copy
@@ -463,13 +580,16 @@ def run_b200(args):
             fill_ms.append(ev0.elapsed_time(ev1))
         write_peak = (1 << 30) / (min(fill_ms) * 1e-3) / 1e9
         del probe
+        wgbs = wbytes * n * kr / (rms * 1e-3) / 1e9
         rollout = {"value": world * n * kr / (rms * 1e-3), "unit": "env-steps/s", "steps_per_launch": kr,
                    "ms_per_launch": rms, "algorithmic_bytes_per_env_step": rbytes,
-                   "achieved_gbs": rbytes * n * kr / (rms * 1e-3) / 1e9, "frac": rbytes * n * kr / (rms * 1e-3) / 1e9 / peak,
-                   "write_gbs": wbytes * n * kr / (rms * 1e-3) / 1e9, "hbm_write_only_gbs_measured": write_peak,
+                   "write_gbs": wgbs, "hbm_write_only_gbs_measured": write_peak,
+                   "frac_of_write_peak": wgbs / write_peak,
+                   "achieved_gbs": rbytes * n * kr / (rms * 1e-3) / 1e9, "frac_of_copy_peak": rbytes * n * kr / (rms * 1e-3) / 1e9 / peak,
                    "api": "gymrs_rollout: one launch, state in registers, actions in / obs, reward, done out per step "
                           f"({kr * (ROLLOUT_BYTES[env]) * n / 1e6:.0f} MB streamed per launch, larger than L2); "
-                          "write-dominated, so its ceiling is the write-only HBM rate, not the copy rate `frac` uses"}
+                          "write-dominated, so the primary figure is frac_of_write_peak (against the write-only HBM rate "
+                          "measured in this run), the copy-peak fraction is given for context"}
         del acts, obs_out, rew_out, done_out
 
     cpu = None
@@ -486,33 +606,36 @@ def run_b200(args):
             "n_gpus": world, "steps": K, "warmup": max(W, 3), "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": WORKLOAD[env], "envs_per_gpu": n, "launch": "one step kernel per step (gymrs_step); the "
-                f"independent ring slots alternate over {len(streams)} CUDA stream(s) so consecutive launches overlap; "
-                f"pdl={args.pdl}", "l2_policy": f"inputs larger than L2: ring of {args.ring} independent "
-                f"{n}-env batches ({args.ring * FOOTPRINT[env] * n / 1e6:.0f} MB footprint) stepped "
-                "round-robin, so every launch touches cold HBM lines",
+            "config": config_of(args, world),
+            "method": {
+                "launch": "one step kernel per step (gymrs_step); the independent ring slots alternate over "
+                          f"{len(streams)} CUDA stream(s) so consecutive launches overlap; pdl={args.pdl}",
                 "repeats": repeats, "timing": "CUDA events on the main stream (the other streams fork from the start "
-                "event and join before the end event), median of repeats, max over ranks",
-                "parallelism": f"env batch sharded over {world} GPU(s), no collective on the step path",
-            },
+                "event and join before the end event), barrier + device synchronize on both sides of every region, "
+                "median of repeats of the element-wise max over ranks"},
+            "timing_sanity": {"regions": sanity["regions"], "device_ms_total": sanity["device_ms"],
+                              "host_ms_total": sanity["host_ms"],
+                              "device_over_host": sanity["device_ms"] / max(sanity["host_ms"], 1e-9),
+                              "note": "host clock from the first launch of a region to the drained device (barriers "
+                                      "excluded); recorded, never asserted"},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(env), "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": ALGO_BYTES[env], "kernel": "step_kernel"},
+                         "algorithmic_bytes_per_env_step": ALGO_BYTES[env], "kernel": "step_kernel",
+                         "kernel_us_isolated": kernel_isolated_us(env)},
             "cpu_baseline": cpu,
             "rollout": rollout,
-            "single_stream_chained": {"value": world * n * K / (statistics.median(chained) * 1e-3), "unit": "env-steps/s",
-                                      "ms_per_step": statistics.median(chained) / K,
-                                      "frac": ALGO_BYTES[env] * n * K / (statistics.median(chained) * 1e-3) / 1e9 / peak,
-                                      "note": "same cold ring on ONE stream with pipelined launches (pdl=2, per-CTA "
-                                              "release/acquire flags instead of a grid-wide dependency)"},
-            "l2_resident": {"value": world * n * K / (statistics.median(resident) * 1e-3), "unit": "env-steps/s",
-                            "ms_per_step": ms_res / K,
-                            "note": "ONE 1M-env batch stepped back to back on one stream, pdl=2 (a true dependency "
-                                    "chain; the state stays in the 126 MB L2); not an HBM number"},
+            "single_stream_default": {
+                "cold_ring": figure(default_cold, "cold ring on ONE stream, pdl=1 (the library default): every launch "
+                                    "waits for the whole previous grid -- what Env::step sees inside a policy loop"),
+                "l2_resident": figure(default_res, "ONE 1M-env batch stepped back to back, pdl=1; the state stays in "
+                                      "the 126 MB L2, so this is not an HBM number")},
+            "single_stream_chained": figure(chained, "same cold ring on ONE stream with pipelined launches (pdl=2, per-CTA "
+                                            "release/acquire flags instead of a grid-wide dependency; needs pre-generated actions)"),
+            "l2_resident": figure(resident, "ONE 1M-env batch stepped back to back on one stream, pdl=2 (a true "
+                                  "dependency chain; the state stays in the 126 MB L2); not an HBM number"),
             "all_ms_per_step": [t / K for t in times][:40],
             "ms_per_step_min_max": [min(times) / K, max(times) / K],
         }
@@ -520,16 +643,26 @@ def run_b200(args):
     for e, _ in ring:
         e.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
     args = parse()
     quiet_stdout()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    except BaseException as exc:  # noqa: BLE001 - the launcher's summary hides tracebacks: say why, last
+        if isinstance(exc, SystemExit) and exc.code in (0, None):
+            raise
+        import traceback
+        traceback.print_exc()
+        sys.stderr.write(f"rank {dist_env()[0]}: bench.py failed: {type(exc).__name__}: {exc}\n")
+        sys.stderr.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":

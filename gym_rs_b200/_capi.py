@@ -14,6 +14,7 @@ OK, ERR_INVALID_ACTION, ERR_BAD_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC, ERR_UNS
 CARTPOLE, MOUNTAIN_CAR, PENDULUM = 0, 1, 2
 FLAG_TIME_LIMIT = 0x1
 STEP_AUTORESET = 0x1
+HOST_U8_ACTIONS, HOST_PACKED_DONE = 0x1, 0x2
 
 
 class CartPoleParams(C.Structure):
@@ -50,6 +51,15 @@ class CheckpointInfo(C.Structure):
                 ("bytes", C.c_uint64)]
 
 
+HOST_STEP_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint32)
+
+
+class HostRolloutDesc(C.Structure):
+    _fields_ = [("actions", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
+                ("truncated", C.c_void_p), ("action_slots", C.c_uint32), ("result_slots", C.c_uint32),
+                ("transport", C.c_uint32), ("_pad", C.c_uint32), ("on_step", HOST_STEP_FN), ("user", C.c_void_p)]
+
+
 _vp, _u64, _u32, _i = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
 _pu64 = C.POINTER(C.c_uint64)
 
@@ -71,6 +81,7 @@ SIGNATURES = {
     "gymrs_step_host": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "gymrs_step_host_async": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _pu64]),
     "gymrs_host_wait": (_i, [_vp, _u64]),
+    "gymrs_rollout_host": (_i, [_vp, _u32, _u32, C.POINTER(HostRolloutDesc)]),
     "gymrs_rollout": (_i, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "gymrs_get_state": (_i, [_vp, _vp, _vp]),
     "gymrs_set_state": (_i, [_vp, _vp, _vp]),

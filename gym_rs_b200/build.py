@@ -41,8 +41,19 @@ def _extra() -> list:
     return shlex.split(os.environ.get("GYMRS_NVCC_EXTRA", ""))
 
 
+STAMP = LIB + ".flags"
+
+
+def _flag_stamp() -> str:
+    """The effective nvcc command line: a library built with other flags (an experiment through
+    GYMRS_NVCC_EXTRA, say) is stale for a plain build and the other way round."""
+    return " ".join(NVCC_FLAGS + _extra())
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
+        return True
+    if open(STAMP).read() != _flag_stamp():
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [
@@ -58,7 +69,7 @@ def _run(cmd):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale() and not os.environ.get("GYMRS_NVCC_EXTRA"):
+    if not force and not _stale():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
@@ -69,6 +80,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         logs = list(ex.map(_run, cmds))
     _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
           "-o", LIB] + objs)
+    with open(STAMP, "w") as f:
+        f.write(_flag_stamp())
     if verbose:
         print("\n".join(logs))
     return LIB

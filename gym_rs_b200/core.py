@@ -123,10 +123,18 @@ class Env(EnvProperties):
         self._refresh_spaces()
         # The device views above are torch tensors and callers produce actions with torch, so the
         # handle must run in torch's stream order, not on its private non-blocking stream.
-        import torch
-        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._stream_seen = None
+        self._follow_stream()
 
     # ---- plumbing ------------------------------------------------------------------
+    def _follow_stream(self):
+        """Keep the handle on torch's CURRENT stream of its device: step / rollout / reset call this
+        first, so `with torch.cuda.stream(s):` and `torch.cuda.graph(...)` blocks order (or capture)
+        the env's kernels like any torch op.  Switching is asynchronous (an event dependency from
+        the old stream to the new one, gymrs_set_stream)."""
+        cur = _current_raw_stream(self.device)
+        if cur != self._stream_seen:
+            self.set_stream(cur)
     def _refresh_views(self):
         b = _capi.Buffers()
         _capi.check(self._L.gymrs_get_buffers(self._h, C.byref(b)))
@@ -179,6 +187,8 @@ class Env(EnvProperties):
         else:
             ptr = int(cuda_stream) or 0x1  # cudaStreamLegacy
         _capi.check(self._L.gymrs_set_stream(self._h, C.c_void_p(ptr)))
+        # a caller-chosen stream is followed until torch's current stream changes again
+        self._stream_seen = None if cuda_stream is None else _current_raw_stream(self.device)
 
     def set_launch_config(self, vec: int = 0, block: int = 0, pdl: int = 1):
         _capi.check(self._L.gymrs_set_launch_config(self._h, vec, block, pdl))
@@ -259,6 +269,8 @@ class Env(EnvProperties):
         if action is not self._checked_action:
             self._check_actions(action)
             self._checked_action = action
+        if _current_raw_stream(self.device) != self._stream_seen:
+            self._follow_stream()
         rc = self._L.gymrs_step(self._h, action.data_ptr(), flags)
         if rc:
             _capi.check(rc)
@@ -300,10 +312,38 @@ class Env(EnvProperties):
     def host_wait(self, ticket: int):
         _capi.check(self._L.gymrs_host_wait(self._h, int(ticket)))
 
+    def rollout_host(self, actions, obs=None, reward=None, done=None, truncated=None, n_steps=None,
+                     autoreset: bool = True, on_step=None, u8_actions: bool = False, packed_done: bool = False):
+        """gymrs_rollout_host: the host loop of examples/cartpole.rs:15-30 over the whole batch, run
+        inside the library.  actions: HOST [action_slots, num_envs]; obs [result_slots, obs_dim,
+        num_envs], reward / done / truncated [result_slots, num_envs] (pinned torch or numpy; done /
+        truncated are [result_slots, ceil(num_envs / 8)] bit rows with packed_done).  Step t reads
+        action slot t % action_slots and fills result slot t % result_slots; on_step(t, slot) is
+        called in step order once the slot is complete."""
+        def hp(a):
+            if a is None:
+                return None
+            return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        slots = [int(a.shape[0]) for a in (obs, reward, done, truncated) if a is not None]
+        if len(set(slots)) > 1:
+            raise ValueError("result buffers must have the same number of slots")
+        d = _capi.HostRolloutDesc()
+        d.actions, d.obs, d.reward, d.done, d.truncated = hp(actions), hp(obs), hp(reward), hp(done), hp(truncated)
+        d.action_slots = int(actions.shape[0])
+        d.result_slots = slots[0] if slots else 2
+        d.transport = (_capi.HOST_U8_ACTIONS if u8_actions else 0) | (_capi.HOST_PACKED_DONE if packed_done else 0)
+        cb = _capi.HOST_STEP_FN(lambda _user, t, slot: on_step(int(t), int(slot))) if on_step else _capi.HOST_STEP_FN()
+        d.on_step = cb
+        flags = _capi.STEP_AUTORESET if autoreset else 0
+        self._follow_stream()
+        _capi.check(self._L.gymrs_rollout_host(self._h, int(n_steps if n_steps is not None else d.action_slots),
+                                               flags, C.byref(d)))
+
     def rollout(self, actions, obs_out=None, reward_out=None, done_out=None, autoreset: bool = True):
         """gymrs_rollout: actions [n_steps, num_envs] on the device; fused multi-step launch."""
         n_steps = int(actions.shape[0])
         self._check_actions(action=actions, steps=n_steps)
+        self._follow_stream()
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         flags = _capi.STEP_AUTORESET if autoreset else 0
         _capi.check(self._L.gymrs_rollout(self._h, p(actions), n_steps, flags, p(obs_out), p(reward_out),
@@ -326,6 +366,7 @@ class Env(EnvProperties):
             if lo.size != self.state_dim or hi.size != self.state_dim:
                 raise ValueError("options bounds must have state_dim entries")
         used = C.c_uint64()
+        self._follow_stream()
         _capi.check(self._L.gymrs_reset(
             self._h, ps, None if lo is None else lo.ctypes.data_as(C.c_void_p),
             None if hi is None else hi.ctypes.data_as(C.c_void_p),
@@ -333,8 +374,14 @@ class Env(EnvProperties):
         self._seed_used = int(used.value)
         info = () if return_info else None  # cartpole.rs:511-515
         if self.num_envs == 1:
-            return self.state, info
+            return self._scalar_observation(), info  # the Observation type, like step() (core.rs:45-50)
         return self._t_obs, info
+
+    def _scalar_observation(self):
+        if self.OBSERVATION is self.STATE:
+            return self.state
+        self.sync()
+        return self.OBSERVATION(*[float(v) for v in self._t_obs[:, 0].cpu()])
 
     def render(self, mode: RenderMode = RenderMode.NONE):
         return Renders.NONE  # renderer.rs:52-61 under RenderMode::None
@@ -352,8 +399,8 @@ class Env(EnvProperties):
         other._h = C.c_void_p()
         _capi.check(self._L.gymrs_clone(self._h, C.byref(other._h)))
         other._refresh_views()
-        import torch
-        other.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        other._stream_seen = None
+        other._follow_stream()
         return other
 
     def serialize(self):
@@ -406,7 +453,8 @@ class Env(EnvProperties):
                                                     C.byref(self._h)))
         self._refresh_views()
         self._refresh_spaces()
-        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._stream_seen = None
+        self._follow_stream()
         return self
 
     def __del__(self):
@@ -424,6 +472,15 @@ def checkpoint_info(blob) -> dict:
     info = _capi.CheckpointInfo()
     _capi.check(_capi.load().gymrs_checkpoint_info_of(buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(info)))
     return {k: int(getattr(info, k)) for k, _ in info._fields_}
+
+
+def _current_raw_stream(device: int) -> int:
+    """torch's current stream on `device` as the integer gymrs_set_stream takes (0 = legacy default)."""
+    import torch
+    try:
+        return int(torch._C._cuda_getCurrentRawStream(device))
+    except AttributeError:  # pragma: no cover - older torch
+        return int(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _obs_values(o):

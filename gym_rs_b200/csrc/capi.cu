@@ -123,6 +123,8 @@ struct gymrs_env {
     int32_t *sbt = nullptr;
     uint32_t *elapsed = nullptr;
     void *d_actions = nullptr; // staging for *_host entry points
+    uint8_t *d_actions8 = nullptr;  // GYMRS_HOST_U8_ACTIONS: the uint8 form as it arrives, two buffers
+    uint8_t *d_done_bits = nullptr, *d_trunc_bits = nullptr; // GYMRS_HOST_PACKED_DONE: bit rows, ld / 8 bytes each
     uint32_t *err_host = nullptr, *err_dev = nullptr;
     // chained launches (kernels_impl.cuh): word [0] = "protocol broken", words [1..] = per-CTA flags
     uint32_t *chain_mem = nullptr;
@@ -150,6 +152,8 @@ struct gymrs_env {
     uint64_t *epoch_mem = nullptr;
     uint64_t epoch_slots = 0;
     bool device_counted = false;
+    uint64_t generation = 0; // see BatchArgs::generation
+    cudaEvent_t switch_ev = nullptr; // orders a new stream after the old one (gymrs_set_stream)
     bool sbt_dirty = false;  // some env may hold steps_beyond_terminated = Some(_)
     int vec = 0, block = 0, pdl = 1;
 };
@@ -232,6 +236,7 @@ BatchArgs base_args(const gymrs_env *e)
     a.rk = philox_round_keys(e->seed);
     a.epoch = e->step_count + 1;
     a.epoch_dev = e->epoch_mem;
+    a.generation = e->generation;
     a.epoch_slots = e->epoch_slots;
     a.epoch_from_dev = e->device_counted ? 1 : 0;
     a.err = e->err_dev;
@@ -383,9 +388,10 @@ int begin_device_counting(gymrs_env *e)
     if (e->host_inflight) return fail(GYMRS_ERR_UNSUPPORTED, "a host step is in flight: gymrs_host_wait before capturing");
     uint64_t *stage = reinterpret_cast<uint64_t *>(e->err_host + 8);
     stage[0] = e->seed;
+    stage[1] = e->generation;
     cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
     CU(cudaThreadExchangeStreamCaptureMode(&mode));
-    cudaError_t ce = cudaMemcpyAsync(e->epoch_mem + 2, stage, sizeof(uint64_t), cudaMemcpyHostToDevice, e->copy_streams[0]);
+    cudaError_t ce = cudaMemcpyAsync(e->epoch_mem + 2, stage, 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, e->copy_streams[0]);
     if (ce == cudaSuccess) ce = fill_step_count(e, e->step_count, e->copy_streams[0]);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->copy_streams[0]);
     cudaThreadExchangeStreamCaptureMode(&mode);
@@ -403,11 +409,36 @@ int refresh_step_count(gymrs_env *e)
     return GYMRS_OK;
 }
 
-void after_step(gymrs_env *e, uint32_t step_flags, uint32_t n_steps)
+// Something a captured launch froze on the host has changed (see BatchArgs::generation): graphs
+// recorded earlier now raise a sticky error when replayed.  The new value is raised on the device
+// by a one-thread kernel on the handle's stream, so it is ordered like the call that caused it and,
+// inside a capture, becomes part of the recording (max: replaying an old recording never lowers it).
+__global__ void raise_generation_kernel(uint64_t *epoch_mem, uint64_t generation)
 {
-    e->step_count += n_steps;
-    if (e->kind == GYMRS_CARTPOLE && !(step_flags & GYMRS_STEP_AUTORESET)) e->sbt_dirty = true;
+    if (epoch_mem[3] < generation) epoch_mem[3] = generation;
 }
+
+cudaError_t bump_generation(gymrs_env *e)
+{
+    e->generation += 1;
+    if (!e->device_counted) return cudaSuccess; // nothing recorded yet: the hand-over writes the value
+    raise_generation_kernel<<<1, 1, 0, e->stream>>>(e->epoch_mem, e->generation);
+    return cudaGetLastError();
+}
+
+// Before the launch arguments of a step are built: the first CartPole step without auto-reset
+// makes steps_beyond_terminated matter, so auto-reset steps must clear it from now on (the SBT
+// kernel variant); a graph that recorded the cheaper variant is stale.
+cudaError_t before_step(gymrs_env *e, uint32_t step_flags)
+{
+    if (e->kind == GYMRS_CARTPOLE && !(step_flags & GYMRS_STEP_AUTORESET) && !e->sbt_dirty) {
+        e->sbt_dirty = true;
+        return bump_generation(e);
+    }
+    return cudaSuccess;
+}
+
+void after_step(gymrs_env *e, uint32_t n_steps) { e->step_count += n_steps; }
 
 int free_env(gymrs_env *e)
 {
@@ -423,11 +454,15 @@ int free_env(gymrs_env *e)
     cudaFree(e->sbt);
     cudaFree(e->elapsed);
     cudaFree(e->d_actions);
+    cudaFree(e->d_actions8);
+    cudaFree(e->d_done_bits);
+    cudaFree(e->d_trunc_bits);
     cudaFree(e->chain_mem);
     cudaFree(e->epoch_mem);
     if (e->err_host) cudaFreeHost(e->err_host);
     for (auto &s : e->copy_streams) if (s) cudaStreamDestroy(s);
     for (auto &v : e->hev) if (v) cudaEventDestroy(v);
+    if (e->switch_ev) cudaEventDestroy(e->switch_ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return GYMRS_OK;
@@ -442,6 +477,7 @@ int alloc_env(gymrs_env *e)
     CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
     for (auto &s : e->copy_streams) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e->switch_ev, cudaEventDisableTiming));
     CU(cudaMalloc(&e->state, sizeof(float) * e->state_dim * e->ld));
     CU(cudaMemsetAsync(e->state, 0, sizeof(float) * e->state_dim * e->ld, e->stream));
     if (e->kind == GYMRS_PENDULUM) {
@@ -600,6 +636,7 @@ int gymrs_clone(const gymrs_env *src, gymrs_env **out)
     e->seed = src->seed; e->step_count = src->step_count; e->sbt_dirty = src->sbt_dirty;
     e->vec = src->vec; e->block = src->block; e->pdl = src->pdl;
     e->device_counted = src->device_counted;
+    e->generation = src->generation;
     int rc = alloc_env(e);
     if (rc != GYMRS_OK) {
         std::string msg = g_last_error;
@@ -619,7 +656,7 @@ int gymrs_clone(const gymrs_env *src, gymrs_env **out)
     cp(e->truncated, src->truncated, e->ld);
     cp(e->sbt, src->sbt, sizeof(int32_t) * e->ld);
     cp(e->elapsed, src->elapsed, sizeof(uint32_t) * e->ld);
-    cp(e->epoch_mem + 2, src->epoch_mem + 2, sizeof(uint64_t)); // the seed
+    cp(e->epoch_mem + 2, src->epoch_mem + 2, 2 * sizeof(uint64_t)); // the seed and the parameter generation
     if (ce == cudaSuccess && src->device_counted) {
         // copy 0 of the source is always current: take the count from it and fill every copy
         ce = cudaMemcpyAsync(&e->step_count, src->epoch_mem + 4, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream);
@@ -642,6 +679,8 @@ int gymrs_set_params(gymrs_env *e, const void *params)
     else if (e->kind == GYMRS_MOUNTAIN_CAR) e->mc = *(const gymrs_mountain_car_params *)params;
     else e->pd = *(const gymrs_pendulum_params *)params;
     fold_params(e);
+    ON_DEVICE(e->device);
+    CU(bump_generation(e)); // graphs recorded under the old constants report GYMRS_ERR_UNSUPPORTED when replayed
     return GYMRS_OK;
 }
 
@@ -657,11 +696,27 @@ int gymrs_get_params(const gymrs_env *e, void *params)
 int gymrs_set_stream(gymrs_env *e, void *cuda_stream)
 {
     if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    if (next == e->stream) return GYMRS_OK;
     if (int rc_ = refuse_in_capture(e, "gymrs_set_stream")) return rc_;
     ON_DEVICE(e->device);
     if (int rc_ = drain_host(e)) return rc_;
-    CU(cudaStreamSynchronize(e->stream));
-    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    // Work already queued on the old stream precedes whatever the handle does on the new one: an
+    // event dependency, not a host synchronisation.  If the new stream is recording a CUDA graph,
+    // earlier work cannot become a dependency of the graph and no synchronising call is allowed;
+    // torch.cuda.graph() synchronises the device before it starts recording, any other caller
+    // must have done the same.
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(next, &st) != cudaSuccess) {
+        cudaGetLastError();
+        st = cudaStreamCaptureStatusNone;
+    }
+    if (st != cudaStreamCaptureStatusActive) {
+        CU(cudaEventRecord(e->switch_ev, e->stream));
+        CU(cudaStreamWaitEvent(next, e->switch_ev, 0));
+    }
+    e->stream = next;
+    e->chain_ok = false;
     return GYMRS_OK;
 }
 
@@ -734,6 +789,7 @@ int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
     if (capturing(e))
         if (int rc_ = begin_device_counting(e)) return rc_;
     if (int rc_ = drain_host(e)) return rc_;
+    CU(before_step(e, step_flags));
     BatchArgs a = base_args(e);
     a.actions = actions;
     LaunchOpts o = make_opts(e, step_flags);
@@ -753,7 +809,7 @@ int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
     e->chain_ok = a.publish != 0; // a pdl == 2 step publishes its flags, chained or not
     e->chain_flag_envs = fe;
     e->chain_stream = e->stream;
-    after_step(e, step_flags, 1);
+    after_step(e, 1);
     return GYMRS_OK;
 }
 
@@ -766,12 +822,52 @@ int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
 // here blocks the host, step t + 1 can be submitted while step t's results are still streaming
 // out: the D2H engine (the bottleneck at 21 B per env-step vs 4 B in) never idles.  Chunk
 // boundaries are multiples of 1024 envs so every chunk keeps the 128-bit access path.
-int gymrs_step_host_async(gymrs_env *e, const void *actions, uint32_t step_flags,
-                          float *obs, float *reward, uint8_t *done, uint8_t *truncated, uint64_t *ticket)
+} // extern "C"
+
+namespace {
+
+// compact wire formats of the host path (GYMRS_HOST_U8_ACTIONS / GYMRS_HOST_PACKED_DONE): tiny
+// conversion kernels next to the copies, so the step kernel itself keeps one action type
+__global__ void widen_u8_kernel(const uint8_t *__restrict__ in, int32_t *__restrict__ out, uint64_t n)
+{
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 4 <= n) {
+        const uchar4 v = *reinterpret_cast<const uchar4 *>(in + i);
+        *reinterpret_cast<int4 *>(out + i) = make_int4(v.x, v.y, v.z, v.w);
+    } else {
+        for (uint64_t j = i; j < n; ++j) out[j] = in[j];
+    }
+}
+// flag bytes (0 / 1) -> bits, byte i/8 bit i%8
+__global__ void pack_bits_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint64_t n)
+{
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i >= n) return;
+    uint32_t bits = 0;
+    if (i + 8 <= n) {
+        const uint2 w = *reinterpret_cast<const uint2 *>(in + i);
+        // four 0/1 bytes -> a nibble: the multiply moves byte k's bit to position 24 + k, no carries
+        bits = (((w.x & 0x01010101u) * 0x01020408u) >> 24 & 0xFu) | ((((w.y & 0x01010101u) * 0x01020408u) >> 24 & 0xFu) << 4);
+    } else {
+        for (uint64_t j = i; j < n; ++j) bits |= (in[j] ? 1u : 0u) << (j - i);
+    }
+    out[i >> 3] = (uint8_t)bits;
+}
+
+int host_step_submit(gymrs_env *e, const void *actions, uint32_t step_flags, uint32_t transport,
+                     float *obs, float *reward, uint8_t *done, uint8_t *truncated, uint64_t *ticket)
 {
     if (!e || !actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
     if (int rc_ = refuse_in_capture(e, "gymrs_step_host")) return rc_;
+    if (transport & ~(GYMRS_HOST_U8_ACTIONS | GYMRS_HOST_PACKED_DONE)) return fail(GYMRS_ERR_BAD_ARG, "unknown transport flag");
+    const bool u8 = (transport & GYMRS_HOST_U8_ACTIONS) != 0, packed = (transport & GYMRS_HOST_PACKED_DONE) != 0;
+    if (u8 && e->kind == GYMRS_PENDULUM) return fail(GYMRS_ERR_UNSUPPORTED, "GYMRS_HOST_U8_ACTIONS needs a discrete action space");
     ON_DEVICE(e->device);
+    if (u8 && !e->d_actions8) CU(cudaMalloc(&e->d_actions8, 2 * e->ld));
+    if (packed && !e->d_done_bits) {
+        CU(cudaMalloc(&e->d_done_bits, e->ld / 8));
+        CU(cudaMalloc(&e->d_trunc_bits, e->ld / 8));
+    }
     if (e->device_counted && !e->host_inflight) {
         // host steps are sliced into several launches that must share one epoch: they are
         // host-counted (from the device's current count), and the new count is written back to
@@ -800,6 +896,7 @@ int gymrs_step_host_async(gymrs_env *e, const void *actions, uint32_t step_flags
     const uint64_t per = ((n + nchunk - 1) / nchunk + 1023) / 1024 * 1024;
     cudaStream_t h2d = e->copy_streams[0], d2h = e->copy_streams[1], cs = e->stream;
     char *staging = (char *)e->d_actions + (size_t)par * 4 * e->ld;
+    CU(before_step(e, step_flags));
     LaunchOpts o = make_opts(e, step_flags);
     o.pdl = 0;
     if (!e->host_inflight) {
@@ -816,32 +913,62 @@ int gymrs_step_host_async(gymrs_env *e, const void *actions, uint32_t step_flags
                     copied = e->hev[HostEv::copied(c)];
         // staging[par] chunk c was last read by the kernel of host step tk - 2
         if (tk >= 2) CU(cudaStreamWaitEvent(h2d, out_ready, 0));
-        CU(cudaMemcpyAsync(staging + 4 * b, (const char *)actions + 4 * b, 4 * cnt, cudaMemcpyHostToDevice, h2d));
+        if (u8)
+            CU(cudaMemcpyAsync(e->d_actions8 + (size_t)par * e->ld + b, (const uint8_t *)actions + b, cnt, cudaMemcpyHostToDevice, h2d));
+        else
+            CU(cudaMemcpyAsync(staging + 4 * b, (const char *)actions + 4 * b, 4 * cnt, cudaMemcpyHostToDevice, h2d));
         CU(cudaEventRecord(in_ready, h2d));
         CU(cudaStreamWaitEvent(cs, in_ready, 0));
+        if (u8) {
+            widen_u8_kernel<<<(unsigned)((cnt + 1023) / 1024), 256, 0, cs>>>(
+                e->d_actions8 + (size_t)par * e->ld + b, reinterpret_cast<int32_t *>(staging + 4 * b), cnt);
+            CU(cudaGetLastError());
+        }
         // the result rows of chunk c are still being copied out for host step tk - 1
         if (e->host_inflight) CU(cudaStreamWaitEvent(cs, copied, 0));
         BatchArgs a = slice_args(e, b, cnt);
         a.epoch_from_dev = 0;
         a.actions = staging + 4 * b;
         CU(do_step(e, a, o, cs, false));
+        if (packed) { // chunk starts are multiples of 1024 envs, so every chunk owns whole bytes
+            const unsigned g = (unsigned)((cnt + 2047) / 2048);
+            if (done) pack_bits_kernel<<<g, 256, 0, cs>>>(e->done + b, e->d_done_bits + b / 8, cnt);
+            if (truncated) pack_bits_kernel<<<g, 256, 0, cs>>>(e->truncated + b, e->d_trunc_bits + b / 8, cnt);
+            CU(cudaGetLastError());
+        }
         CU(cudaEventRecord(out_ready, cs));
         CU(cudaStreamWaitEvent(d2h, out_ready, 0));
         if (obs)
             CU(cudaMemcpy2DAsync(obs + b, sizeof(float) * n, e->obs + b, sizeof(float) * e->ld,
                                  sizeof(float) * cnt, e->obs_dim, cudaMemcpyDeviceToHost, d2h));
         if (reward) CU(cudaMemcpyAsync(reward + b, e->reward + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, d2h));
-        if (done) CU(cudaMemcpyAsync(done + b, e->done + b, cnt, cudaMemcpyDeviceToHost, d2h));
-        if (truncated) CU(cudaMemcpyAsync(truncated + b, e->truncated + b, cnt, cudaMemcpyDeviceToHost, d2h));
+        if (packed) {
+            const size_t nb = (size_t)((cnt + 7) / 8);
+            if (done) CU(cudaMemcpyAsync(done + b / 8, e->d_done_bits + b / 8, nb, cudaMemcpyDeviceToHost, d2h));
+            if (truncated) CU(cudaMemcpyAsync(truncated + b / 8, e->d_trunc_bits + b / 8, nb, cudaMemcpyDeviceToHost, d2h));
+        } else {
+            if (done) CU(cudaMemcpyAsync(done + b, e->done + b, cnt, cudaMemcpyDeviceToHost, d2h));
+            if (truncated) CU(cudaMemcpyAsync(truncated + b, e->truncated + b, cnt, cudaMemcpyDeviceToHost, d2h));
+        }
         CU(cudaEventRecord(copied, d2h));
     }
     CU(cudaEventRecord(e->hev[HostEv::host_done(par)], d2h));
-    after_step(e, step_flags, 1);
+    after_step(e, 1);
     if (e->device_counted) CU(fill_step_count(e, e->step_count, cs)); // the slices were host-counted
     e->host_inflight = true;
     e->host_seq = tk + 1;
     if (ticket) *ticket = tk;
     return GYMRS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int gymrs_step_host_async(gymrs_env *e, const void *actions, uint32_t step_flags,
+                          float *obs, float *reward, uint8_t *done, uint8_t *truncated, uint64_t *ticket)
+{
+    return host_step_submit(e, actions, step_flags, 0u, obs, reward, done, truncated, ticket);
 }
 
 int gymrs_host_wait(gymrs_env *e, uint64_t ticket)
@@ -875,6 +1002,41 @@ int gymrs_step_host(gymrs_env *e, const void *actions, uint32_t step_flags,
     return GYMRS_OK;
 }
 
+// The host loop of examples/cartpole.rs:15-30 for a whole batch, inside the library: step t is
+// submitted while step t - 1 is still streaming out, the consumer sees the steps in order.
+int gymrs_rollout_host(gymrs_env *e, uint32_t n_steps, uint32_t step_flags, const gymrs_host_rollout_desc *d)
+{
+    if (!e || !d || !d->actions) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    if (d->action_slots == 0) return fail(GYMRS_ERR_BAD_ARG, "action_slots must be >= 1");
+    if (d->result_slots < 2) return fail(GYMRS_ERR_BAD_ARG, "result_slots must be >= 2 (step t + 1 is submitted while step t streams out)");
+    const uint64_t n = e->n;
+    const bool u8 = (d->transport & GYMRS_HOST_U8_ACTIONS) != 0, packed = (d->transport & GYMRS_HOST_PACKED_DONE) != 0;
+    const size_t act_stride = (size_t)n * (u8 ? 1 : 4), flag_stride = packed ? (size_t)((n + 7) / 8) : (size_t)n;
+    uint64_t prev = 0;
+    for (uint32_t t = 0; t < n_steps; ++t) {
+        const uint32_t slot = t % d->result_slots;
+        uint64_t tk = 0;
+        int rc = host_step_submit(e, (const char *)d->actions + (size_t)(t % d->action_slots) * act_stride, step_flags, d->transport,
+                                  d->obs ? d->obs + (size_t)slot * e->obs_dim * n : nullptr,
+                                  d->reward ? d->reward + (size_t)slot * n : nullptr,
+                                  d->done ? d->done + (size_t)slot * flag_stride : nullptr,
+                                  d->truncated ? d->truncated + (size_t)slot * flag_stride : nullptr, &tk);
+        if (rc != GYMRS_OK) return rc;
+        if (t > 0) {
+            if (int rc_ = gymrs_host_wait(e, prev)) return rc_;
+            if (d->on_step) d->on_step(d->user, t - 1, (t - 1) % d->result_slots);
+        }
+        prev = tk;
+    }
+    if (n_steps > 0) {
+        if (int rc_ = gymrs_host_wait(e, prev)) return rc_;
+        if (d->on_step) d->on_step(d->user, n_steps - 1, (n_steps - 1) % d->result_slots);
+    }
+    ON_DEVICE(e->device);
+    CU(cudaStreamSynchronize(e->stream));
+    return GYMRS_OK;
+}
+
 int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t step_flags,
                   float *obs_out, float *reward_out, uint8_t *done_out)
 {
@@ -884,6 +1046,7 @@ int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t 
     if (capturing(e))
         if (int rc_ = begin_device_counting(e)) return rc_;
     if (int rc_ = drain_host(e)) return rc_;
+    CU(before_step(e, step_flags));
     BatchArgs a = base_args(e);
     a.actions = actions;
     a.n_steps = n_steps;
@@ -901,7 +1064,7 @@ int gymrs_rollout(gymrs_env *e, const void *actions, uint32_t n_steps, uint32_t 
     if (odd_grid) CU(spread_step_count(e, e->stream));
     CU(do_step(e, a, o, e->stream, true));
     if (odd_grid) CU(spread_step_count(e, e->stream));
-    after_step(e, step_flags, n_steps);
+    after_step(e, n_steps);
     return GYMRS_OK;
 }
 
@@ -1124,6 +1287,8 @@ int gymrs_checkpoint_load(gymrs_env *e, const void *buf, size_t bytes)
     if (l.sbt) CU(cudaMemcpyAsync(e->sbt, in + l.sbt, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
     if (l.elapsed) CU(cudaMemcpyAsync(e->elapsed, in + l.elapsed, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(e->epoch_mem + 2, &h.seed, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    e->generation += 1; // the parameters are replaced below: graphs recorded on this handle are stale
+    CU(cudaMemcpyAsync(e->epoch_mem + 3, &e->generation, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     CU(fill_step_count(e, h.step_count, s));
     CU(cudaStreamSynchronize(s));
     e->global_off = h.global_off;
@@ -1247,6 +1412,11 @@ int gymrs_sync(gymrs_env *e, uint64_t *bad_env)
         e->err_host[5] = 0;
         return fail(GYMRS_ERR_UNSUPPORTED, "a CUDA graph whose steps were captured under a different seed was replayed: "
                     "captured steps bake the handle's Philox key in, so re-capture after re-seeding the handle");
+    }
+    if (e->err_host[6]) {
+        e->err_host[6] = 0;
+        return fail(GYMRS_ERR_UNSUPPORTED, "a CUDA graph recorded before gymrs_set_params (or before the handle's first step without "
+                    "auto-reset) was replayed: captured steps bake the parameter block and the step variant in, so re-capture");
     }
     if (e->err_host[0]) {
         const uint64_t gid = (uint64_t)e->err_host[1] | ((uint64_t)e->err_host[2] << 32);

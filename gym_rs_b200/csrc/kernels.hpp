@@ -33,11 +33,17 @@ struct BatchArgs {
     // dependency wait -- the form a CUDA graph needs, where kernel arguments are frozen at capture
     // but every replay is a new step.
     uint64_t *epoch_dev;
+    // epoch_dev[3] = the handle's parameter generation: bumped whenever something a captured launch
+    // froze on the host changes afterwards (gymrs_set_params, the first non-auto-reset step that
+    // makes steps_beyond_terminated matter).  A device-counted launch compares it with the value it
+    // was recorded under and raises err[6] on a mismatch instead of silently using stale constants.
+    uint64_t generation;
     uint64_t epoch_slots;
     int epoch_from_dev;
     uint32_t *err;       // device-visible words: [0] invalid-action flag, [1..2] one offending global id,
                          // [3] chained-dependency timeout flag, [4] the offending action's bits,
                          // [5] a graph captured under another seed was replayed
+                         // [6] a graph captured under older parameters / step options was replayed
     int early_actions;   // step: read the action row before any dependency is resolved (LaunchOpts::pdl == 2)
     // chained launches: per-CTA progress flags of this handle (see kernels_impl.cuh)
     uint32_t *chain_flags; // [number of CTAs]; CTA b stores chain_seq here when its stores are done

@@ -164,6 +164,9 @@ __device__ __forceinline__ void advance_epoch(const BatchArgs &a, uint64_t first
             // replay drew from the old stream -- raise the sticky error word (gymrs_sync reports it).
             if (blockIdx.x == 0 && __ldcg(a.epoch_dev + 2) != ((uint64_t)a.rk.k[0][0] | ((uint64_t)a.rk.k[0][1] << 32)))
                 *reinterpret_cast<volatile uint32_t *>(a.err + 5) = 1u;
+            // likewise the by-value parameter block and the step variant (capi.cu, bump_generation)
+            if (blockIdx.x == 0 && __ldcg(a.epoch_dev + 3) != a.generation)
+                *reinterpret_cast<volatile uint32_t *>(a.err + 6) = 1u;
         }
     }
 }

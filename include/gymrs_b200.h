@@ -163,6 +163,39 @@ int gymrs_step_host_async(gymrs_env *env, const void *actions, uint32_t step_fla
                           float *obs, float *reward, uint8_t *done, uint8_t *truncated, uint64_t *ticket);
 int gymrs_host_wait(gymrs_env *env, uint64_t ticket);
 
+/* Host-buffer rollout: n_steps pipelined host steps driven from inside the library -- the loop
+ * `for t { reset-on-done by hand; env.step(action) }` of examples/cartpole.rs:15-30 over a whole
+ * batch, with the observation / reward / done of EVERY step delivered to host memory.  Equivalent
+ * to calling gymrs_step_host_async(t) / gymrs_host_wait(t - 1) in a loop, without one FFI crossing
+ * per step (one process per GPU then spends its host core on the consumer, not on the binding).
+ *   step t reads   actions  slot (t % action_slots)
+ *   step t writes  results  slot (t % result_slots), result_slots >= 2
+ * on_step (optional) runs on the calling thread, in step order, as soon as step t's results are
+ * complete in their slot; the slot is reused by step t + result_slots, so consume it before
+ * returning.  Synchronises before it returns.
+ * transport: compact wire formats for the PCIe crossing (lossless; the device unpacks / packs):
+ *   GYMRS_HOST_U8_ACTIONS   discrete actions travel as uint8[num_envs] instead of int32
+ *   GYMRS_HOST_PACKED_DONE  done / truncated travel as bits: byte i/8, bit i%8 (LSB first),
+ *                           ceil(num_envs / 8) bytes per slot */
+#define GYMRS_HOST_U8_ACTIONS 0x1u
+#define GYMRS_HOST_PACKED_DONE 0x2u
+typedef void (*gymrs_host_step_fn)(void *user, uint32_t step, uint32_t slot);
+typedef struct gymrs_host_rollout_desc {
+    const void *actions;   /* host [action_slots][num_envs] */
+    float *obs;            /* host [result_slots][obs_dim][num_envs], or NULL */
+    float *reward;         /* host [result_slots][num_envs], or NULL */
+    uint8_t *done;         /* host [result_slots][num_envs] (or [..][ceil(num_envs/8)] packed), or NULL */
+    uint8_t *truncated;    /* like done, or NULL */
+    uint32_t action_slots;
+    uint32_t result_slots;
+    uint32_t transport;
+    uint32_t _pad;
+    gymrs_host_step_fn on_step;
+    void *user;
+} gymrs_host_rollout_desc;
+int gymrs_rollout_host(gymrs_env *env, uint32_t n_steps, uint32_t step_flags,
+                       const gymrs_host_rollout_desc *desc);
+
 /* Fused rollout: n_steps consecutive steps in ONE launch, state held in registers.
  * actions: device [n_steps][num_envs].  Per-step results are streamed to the caller's
  * device arrays (any may be NULL): obs_out [n_steps][obs_dim][num_envs],

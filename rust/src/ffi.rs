@@ -21,6 +21,26 @@ pub const GYMRS_ERR_UNSUPPORTED: c_int = 6;
 
 pub const GYMRS_FLAG_TIME_LIMIT: u32 = 0x1;
 pub const GYMRS_STEP_AUTORESET: u32 = 0x1;
+pub const GYMRS_HOST_U8_ACTIONS: u32 = 0x1;
+pub const GYMRS_HOST_PACKED_DONE: u32 = 0x2;
+
+pub type gymrs_host_step_fn = Option<unsafe extern "C" fn(user: *mut c_void, step: u32, slot: u32)>;
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct gymrs_host_rollout_desc {
+    pub actions: *const c_void,
+    pub obs: *mut f32,
+    pub reward: *mut f32,
+    pub done: *mut u8,
+    pub truncated: *mut u8,
+    pub action_slots: u32,
+    pub result_slots: u32,
+    pub transport: u32,
+    pub _pad: u32,
+    pub on_step: gymrs_host_step_fn,
+    pub user: *mut c_void,
+}
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
@@ -113,6 +133,8 @@ extern "C" {
     pub fn gymrs_step_host_async(env: *mut gymrs_env, actions: *const c_void, step_flags: u32, obs: *mut f32,
                                  reward: *mut f32, done: *mut u8, truncated: *mut u8, ticket: *mut u64) -> c_int;
     pub fn gymrs_host_wait(env: *mut gymrs_env, ticket: u64) -> c_int;
+    pub fn gymrs_rollout_host(env: *mut gymrs_env, n_steps: u32, step_flags: u32,
+                              desc: *const gymrs_host_rollout_desc) -> c_int;
     pub fn gymrs_rollout(env: *mut gymrs_env, actions: *const c_void, n_steps: u32, step_flags: u32,
                          obs_out: *mut f32, reward_out: *mut f32, done_out: *mut u8) -> c_int;
     pub fn gymrs_get_state(env: *mut gymrs_env, state: *mut f32, sbt: *mut i32) -> c_int;

@@ -36,5 +36,23 @@ def test_bench_line_on_gpu(env):
     ck = d["clocks"]
     assert set(ck) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert not set(ck["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert e2e["pcie_ceiling_gbs"] > 0 and 0 < e2e["frac_of_pcie"] < 1.5
+    if env == "cartpole":
+        assert e2e["compact"]["value"] > 0 and e2e["compact"]["bytes_per_step"] < (4 + 21) * 131072
     for extra in ("single_stream_chained", "l2_resident", "rollout"):
         assert d[extra]["value"] > 0
+    for mode in ("cold_ring", "l2_resident"):
+        assert d["single_stream_default"][mode]["value"] > 0
+    assert d["timing_sanity"]["regions"] > 0 and "method" in d
+    assert d["rollout"]["frac_of_write_peak"] > 0
+
+
+def test_reference_arm_line(tmp_path):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "5",
+                        "--warmup", "2", "--envs", "65536", "--ref-repeats", "3"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]

@@ -89,3 +89,26 @@ def test_one_process_drives_two_devices_without_disturbing_the_current_device():
     assert torch.cuda.current_device() == 0
     for e in (e0, e1, whole):
         e.close()
+
+
+def test_bench_under_torchrun_at_the_drivers_short_step_count():
+    """The driver's scaling run: `torchrun --nproc-per-node N bench.py --gpus N --steps 20 --warmup 5`.
+    A 20-step region is ~0.13 ms of device time, far below the cost of a barrier: the run must still
+    produce exactly one JSON line (round 1 died here on a wall-clock assertion)."""
+    import json
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29583", os.path.join(ROOT, "bench.py"),
+                        "--gpus", "2", "--steps", "20", "--warmup", "5"],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["steps"] == 20 and d["scaling"] == "weak"
+    assert d["value"] > 1.5e11                      # two GPUs, each near the single-GPU rate
+    assert d["e2e"]["value"] > 0 and 0 < d["e2e"]["frac_of_pcie"] < 1.5
+    assert d["timing_sanity"]["regions"] > 0

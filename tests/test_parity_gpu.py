@@ -140,7 +140,8 @@ def test_pendulum_single_step_parity_1m(torch, g):
     # stored theta is wrapped to [-pi, pi): compare modulo 2 pi
     d = gs[0].astype(np.float64) - ref["state"][0]
     d = d - 2 * math.pi * np.round(d / (2 * math.pi))
-    assert np.abs(d).max() <= 4e-6
+    th_err = np.abs(d) / np.maximum(1.0, np.abs(ref["state"][0]))   # the stated metric: 1e-6 * max(1, |ref|)
+    assert th_err.max() <= TOL, th_err.max()
     assert np.abs(gs[0]).max() <= math.pi + 1e-6
     assert_within(gs[1], ref["state"][1], "pendulum theta_dot")
     assert not out.done.cpu().numpy().any()
@@ -317,7 +318,7 @@ def test_appendix_b_exact_cases(torch, g):
 
 @pytest.mark.parametrize("kind", ["cartpole", "mountain_car", "pendulum"])
 def test_closed_loop_trajectory_parity(torch, g, kind):
-    n, steps = 1 << 15, 200
+    n, steps = 1 << 15, 500  # 500-step closed loop with per-step resync
     r = np.random.default_rng(11)
     if kind == "cartpole":
         env, ok = g.CartPoleEnv(num_envs=n), oracle.CARTPOLE
@@ -352,7 +353,7 @@ def test_closed_loop_trajectory_parity(torch, g, kind):
                 rr = out.reward.cpu().numpy()
                 assert np.array_equal(rr[~diff], ref["reward"][~diff].astype(np.float32))
             disagreements += int(diff.sum())
-    assert disagreements < 20
+    assert disagreements < 50
     if kind == "cartpole":
         # without reset practically every pole has fallen: steps_beyond_terminated is Some(_)
         assert (sbt >= 0).mean() > 0.99
@@ -505,7 +506,8 @@ def test_vec_widths_and_ragged_sizes_are_bit_identical(torch, g, kind):
     if kind == "pendulum":
         acts = [dev_actions(torch, r.uniform(-2, 2, n).astype(np.float32)) for _ in range(6)]
     else:
-        acts = [dev_actions(torch, r.integers(0, 2, n).astype(np.int32)) for _ in range(6)]
+        acts = [dev_actions(torch, r.integers(0, 2 if kind == "cartpole" else 3, n).astype(np.int32))
+                for _ in range(6)]
     results = []
     for vec, block in ((4, 256), (2, 128), (1, 64), (0, 0)):
         env = cls(num_envs=n, time_limit=True)
@@ -693,6 +695,175 @@ def test_async_host_pipeline_equals_synchronous_host_steps(torch, g):
     assert torch.equal(out.observation, ob.observation)
     a.close()
     b.close()
+
+
+def test_mountain_car_autoreset_resamples_done_envs_like_the_oracle(torch, g):
+    """BASELINE config 3 (MountainCar, auto-reset on done): envs that reach the goal are re-sampled in
+    the same launch from Philox(seed, global id, epoch = step index + 1); everything else follows
+    mountain_car.rs:398-435."""
+    n = 1 << 16
+    r = np.random.default_rng(31)
+    # near the goal, moving right: a good share of the envs finish in one step
+    st = np.stack([r.uniform(0.40, 0.60, n), r.uniform(-0.02, 0.07, n)]).astype(np.float32)
+    act = r.integers(0, 3, n).astype(np.int32)
+    env = g.MountainCarEnv(num_envs=n, global_env_offset=5000)
+    env.reset(seed=123)
+    env.set_state(st)
+    for epoch in (1, 2):
+        out = env.step(dev_actions(torch, act), autoreset=True)
+        env.sync()
+        ref = oracle.step_batch(oracle.MOUNTAIN_CAR, st, act)
+        gd = out.done.cpu().numpy().astype(bool)
+        rp, rv = ref["state"]
+        band = (np.abs(rp - 0.5) < 1e-6) | (np.abs(rv) < 1e-9)
+        assert np.array_equal(gd[~band], ref["done"][~band].astype(bool))
+        assert gd.mean() > 0.05 if epoch == 1 else True
+        got = out.observation.cpu().numpy()
+        assert_within(got[:, ~gd], ref["state"][:, ~gd], f"surviving envs, step {epoch}")
+        fresh = oracle.reset_batch(oracle.MOUNTAIN_CAR, n, seed=123, global_env_offset=5000, epoch=epoch)
+        assert np.abs(got[0, gd] - fresh[0, gd]).max() <= 1e-7 if gd.any() else True
+        assert np.all(got[1, gd] == 0.0)                                  # mountain_car.rs:162-167
+        assert np.all(out.reward.cpu().numpy() == -1.0)                   # :423, terminal step included
+        assert not out.truncated.cpu().numpy().any()                      # :432
+        st = env.get_state()
+        assert np.array_equal(st, got)
+        # second round: push the fresh envs (which sit in the valley) and the rest once more
+    env.close()
+
+
+def test_pendulum_autoreset_on_truncation_matches_the_oracle(torch, g):
+    """Pendulum never terminates, so its auto-reset fires through the TimeLimit only: at the horizon
+    every env is re-sampled from Philox(seed, global id, epoch = step index + 1) and the returned
+    observation is (cos, sin, theta_dot) of the FRESH state."""
+    n = 1 << 16
+    r = np.random.default_rng(32)
+    env = g.PendulumEnv(num_envs=n, time_limit=True, global_env_offset=77)
+    p = env.params
+    p.max_episode_steps = 3
+    env.params = p
+    env.reset(seed=9)
+    for t in range(1, 8):
+        st = env.get_state()
+        act = r.uniform(-2.5, 2.5, n).astype(np.float32)
+        out = env.step(dev_actions(torch, act), autoreset=True)
+        env.sync()
+        ref = oracle.step_batch(oracle.PENDULUM, st, act)
+        assert_within(out.reward.cpu().numpy(), ref["reward"], f"reward t={t}")  # the cost of the step that ended the episode
+        tr = out.truncated.cpu().numpy().astype(bool)
+        assert tr.all() == (t % 3 == 0) and tr.any() == (t % 3 == 0)
+        assert not out.done.cpu().numpy().any()
+        obs = out.observation.cpu().numpy()
+        if t % 3 == 0:
+            fresh = oracle.reset_batch(oracle.PENDULUM, n, seed=9, global_env_offset=77, epoch=t)
+            gs = env.get_state()
+            assert np.abs(gs - fresh).max() <= 5e-7
+            want = np.stack([np.cos(fresh[0]), np.sin(fresh[0]), fresh[1]])
+            assert_within(obs, want, f"fresh observation t={t}")
+            assert (core_elapsed(env) == 0).all()
+        else:
+            assert_within(obs, ref["obs"], f"obs t={t}")
+    env.close()
+
+
+@pytest.mark.parametrize("kind", ["cartpole", "mountain_car", "pendulum"])
+def test_rollout_host_equals_synchronous_host_steps(torch, g, kind):
+    """gymrs_rollout_host (the pipelined host loop inside the library) delivers, step by step and in
+    order, exactly what gymrs_step_host delivers -- also with the compact wire formats."""
+    n = (1 << 19) + 3 * 1024 + 5
+    cls = {"cartpole": g.CartPoleEnv, "mountain_car": g.MountainCarEnv, "pendulum": g.PendulumEnv}[kind]
+    r = np.random.default_rng(3)
+    steps, S = 7, 3
+    a, b, c = cls(num_envs=n, time_limit=True), cls(num_envs=n, time_limit=True), cls(num_envs=n, time_limit=True)
+    for e in (a, b, c):
+        pp = e.params
+        pp.max_episode_steps = 4
+        e.params = pp
+        e.reset(seed=8)
+    od = a.obs_dim
+    if kind == "pendulum":
+        acts = torch.as_tensor(r.uniform(-2, 2, (steps, n)).astype(np.float32)).pin_memory()
+    else:
+        acts = torch.as_tensor(r.integers(0, 2 if kind == "cartpole" else 3, (steps, n)).astype(np.int32)).pin_memory()
+    obs = torch.empty((S, od, n), dtype=torch.float32).pin_memory()
+    rew = torch.empty((S, n), dtype=torch.float32).pin_memory()
+    done = torch.empty((S, n), dtype=torch.uint8).pin_memory()
+    trunc = torch.empty((S, n), dtype=torch.uint8).pin_memory()
+    seen = []
+
+    def on_step(t, slot):
+        assert slot == t % S
+        seen.append((t, obs[slot].clone(), rew[slot].clone(), done[slot].clone(), trunc[slot].clone()))
+
+    a.rollout_host(acts, obs, rew, done, trunc, autoreset=True, on_step=on_step)
+    assert [t for t, *_ in seen] == list(range(steps))
+    ro, rr, rd, rt = (torch.empty((od, n)), torch.empty(n), torch.empty(n, dtype=torch.uint8),
+                      torch.empty(n, dtype=torch.uint8))
+    for t in range(steps):
+        b.step_host(acts[t], ro, rr, rd, rt, autoreset=True)
+        _, o, w, d, tr = seen[t]
+        assert torch.equal(o, ro) and torch.equal(w, rr) and torch.equal(d, rd) and torch.equal(tr, rt), t
+    assert np.array_equal(a.get_state(), b.get_state())
+    assert any(bool(s[4].any()) for s in seen)          # the horizon of 4 was hit inside the rollout
+    if kind != "pendulum":
+        # compact transport: uint8 actions in, done / truncated as bits out
+        nb = (n + 7) // 8
+        bits_d = torch.empty((S, nb), dtype=torch.uint8).pin_memory()
+        bits_t = torch.empty((S, nb), dtype=torch.uint8).pin_memory()
+        seen_c = []
+
+        def on_step_c(t, slot):
+            seen_c.append((obs[slot].clone(), rew[slot].clone(), bits_d[slot].clone(), bits_t[slot].clone()))
+
+        c.rollout_host(acts.to(torch.uint8).pin_memory(), obs, rew, bits_d, bits_t, autoreset=True, on_step=on_step_c,
+                       u8_actions=True, packed_done=True)
+        for t in range(steps):
+            o, w, bd, bt = seen_c[t]
+            assert torch.equal(o, seen[t][1]) and torch.equal(w, seen[t][2])
+            assert np.array_equal(np.unpackbits(bd.numpy(), bitorder="little")[:n], seen[t][3].numpy())
+            assert np.array_equal(np.unpackbits(bt.numpy(), bitorder="little")[:n], seen[t][4].numpy())
+    else:
+        with pytest.raises(Exception):
+            c.rollout_host(acts, obs, rew, done, trunc, u8_actions=True)
+    for e in (a, b, c):
+        e.close()
+
+
+def test_handle_follows_torch_current_stream(torch, g):
+    """core.py binds the handle to torch's CURRENT stream at every step / rollout / reset: actions
+    produced on a side stream are consumed by a step issued under the same stream context."""
+    n = 1 << 18
+    a, b = g.CartPoleEnv(num_envs=n), g.CartPoleEnv(num_envs=n)
+    a.reset(seed=4)
+    b.reset(seed=4)
+    side = torch.cuda.Stream()
+    gen_a = torch.Generator(device="cuda").manual_seed(9)
+    gen_b = torch.Generator(device="cuda").manual_seed(9)
+    for t in range(40):
+        with torch.cuda.stream(side):
+            act = torch.randint(0, 2, (n,), generator=gen_a, device="cuda", dtype=torch.int32)
+            big = torch.randn(1 << 22, device="cuda").sin_()        # keeps the side stream busy before the step
+            act = act + (big[:n] * 0).to(torch.int32)
+            out = a.step(act, autoreset=True)
+        ptr = C_void(a)
+        assert ptr == side.cuda_stream
+        act_b = torch.randint(0, 2, (n,), generator=gen_b, device="cuda", dtype=torch.int32)
+        ob = b.step(act_b, autoreset=True)
+        assert C_void(b) == torch.cuda.current_stream().cuda_stream
+    side.synchronize()
+    a.sync()
+    b.sync()
+    assert np.array_equal(a.get_state(), b.get_state())
+    a.close()
+    b.close()
+
+
+def C_void(env):
+    import ctypes
+    p = ctypes.c_void_p()
+    from gym_rs_b200 import _capi
+    _capi.check(_capi.load().gymrs_get_stream(env.handle, ctypes.byref(p)))
+    v = p.value or 0
+    return 0 if v == 1 else v   # cudaStreamLegacy is how stream 0 is passed down
 
 
 def test_sharding_invariance_at_full_size(torch, g):
