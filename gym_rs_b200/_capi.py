@@ -117,7 +117,8 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    # GYMRS_LIB_PATH: an experimental build of the same sources (tools/build_variant.py), for A/B runs
+    path = os.environ.get("GYMRS_LIB_PATH") or _build.build()
     if not os.path.exists(path):
         raise ImportError("libgymrs_b200.so is missing and could not be built")
     L = C.CDLL(path)

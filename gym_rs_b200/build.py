@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "libgymrs_b200.so")
 SOURCES = ["kernels_cartpole.cu", "kernels_mountain_car.cu", "kernels_pendulum.cu", "capi.cu"]
-HEADERS = ["kernels_impl.cuh", "kernels.hpp", "envs.cuh", "philox.cuh",
+HEADERS = ["kernels_impl.cuh", "kernels.hpp", "envs.cuh", "lanes.cuh", "philox.cuh",
            os.path.join(ROOT, "include", "gymrs_b200.h")]
 
 NVCC_FLAGS = [

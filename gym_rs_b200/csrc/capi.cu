@@ -184,7 +184,7 @@ void fold_params(gymrs_env *e)
         d.pml_over_m = (float)(polemass_length / total_mass);
         d.gravity = (float)p.gravity;
         d.den_a = (float)(p.length * (4.0 / 3.0));
-        d.den_b = (float)(p.length * p.masspole / total_mass);
+        d.neg_den_b = (float)(-(p.length * p.masspole / total_mass));
         d.x_thr = f32_floor(p.x_threshold);
         d.th_thr = f32_floor(p.theta_threshold_radians);
         d.semi_implicit = p.kinematics_integrator != 0;
@@ -576,7 +576,9 @@ int gymrs_create(int kind, uint64_t num_envs, int device, uint64_t global_env_of
     *out = nullptr;
     if (kind < GYMRS_CARTPOLE || kind > GYMRS_PENDULUM) return fail(GYMRS_ERR_BAD_ARG, "unknown env kind");
     if (num_envs == 0) return fail(GYMRS_ERR_BAD_ARG, "num_envs must be > 0");
-    if (num_envs > (1ull << 40)) return fail(GYMRS_ERR_BAD_ARG, "num_envs too large");
+    // the kernels index the envs of one launch with 32 bits; larger batches are several handles
+    // (global_env_offset keeps their reset streams disjoint)
+    if (num_envs > (1ull << 31)) return fail(GYMRS_ERR_BAD_ARG, "num_envs too large: at most 2^31 envs per handle");
     int ndev = gymrs_device_count();
     if (ndev <= 0) return fail(GYMRS_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
     if (device < 0 || device >= ndev) return fail(GYMRS_ERR_BAD_ARG, "device ordinal out of range");
@@ -1178,7 +1180,7 @@ int ckpt_parse(const void *buf, size_t bytes, CkptHeader *h)
     std::memcpy(h, buf, sizeof *h);
     if (std::memcmp(h->magic, CKPT_MAGIC, 8) != 0) return fail(GYMRS_ERR_BAD_ARG, "not a gymrs checkpoint (bad magic)");
     if (h->version != CKPT_VERSION) return fail(GYMRS_ERR_UNSUPPORTED, "unsupported checkpoint version");
-    if (h->kind > (uint32_t)GYMRS_PENDULUM || h->n == 0 || h->n > (1ull << 40))
+    if (h->kind > (uint32_t)GYMRS_PENDULUM || h->n == 0 || h->n > (1ull << 31))
         return fail(GYMRS_ERR_BAD_ARG, "corrupt checkpoint header");
     const CkptLayout l = ckpt_layout((int)h->kind, h->n, h->flags);
     if (h->total_bytes != l.total || bytes < l.total) return fail(GYMRS_ERR_BAD_ARG, "checkpoint blob is truncated");

@@ -6,7 +6,14 @@
 //   HAS_SBT          keeps the reference's steps_beyond_terminated (CartPole)
 //   Action, P        action element type, by-value parameter block
 //   valid()          Space::contains on the action      (spaces/discrete.rs:14-20)
-//   step()           one env transition on registers
+//   pre()            the per-env action term the dynamics consume (force, push, clamped torque)
+//   fast_ok()        this env may take the straight-line path (small angle / bounded argument)
+//   advance<Lane>()  the dynamics, written once against an arithmetic lane (lanes.cuh): Lane2 steps
+//                    TWO envs per instruction with packed fp32 (FFMA2), Lane1 is the scalar form;
+//                    both round identically
+//   advance_slow()   scalar, any argument (full-range libm trig)
+//   terminal()       done flag of the post-step state
+//   step()           pre + advance (fast or slow) + terminal for one env on registers
 //   reset()          fresh state from 4 Philox words
 //
 // The arithmetic is NOT a transliteration of the Rust lines: constants that the
@@ -18,6 +25,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "lanes.cuh"
 #include "philox.cuh"
 
 namespace gymrs {
@@ -28,32 +36,15 @@ struct ResetBox {
     float cap[4];   // largest float below high
 };
 
-// num / den as MUFU.RCP plus one Newton correction on the quotient (4 instructions, result
-// within 1 ulp for normal operands) instead of the ~10-instruction IEEE division sequence with
-// its slow-path call.  A zero / non-finite den yields inf or NaN (never a finite wrong value).
-__device__ __forceinline__ float div_newton(float num, float den)
+// num / den on a lane: MUFU.RCP plus one Newton correction on the quotient (result within 1 ulp for
+// normal operands) instead of the ~10-instruction IEEE division sequence with its slow-path call.
+// A zero / non-finite den yields inf or NaN (never a finite wrong value).
+template <class L>
+__device__ __forceinline__ typename L::T div_newton(typename L::T num, typename L::T den)
 {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
-    const float q = num * r;
-    return fmaf(fmaf(-den, q, num), r, q);
-}
-
-// sin and cos of a pole angle.  A live CartPole has |theta| <= 0.21 (+ one step), so the common
-// case needs neither range reduction nor quadrant selection: two short minimax polynomials on
-// [-pi/4, pi/4] (Cephes sinf/cosf coefficients, <= 1 ulp there).  Anything larger (a pole that
-// keeps falling when the caller never resets) takes the full-range sincosf.
-__device__ __forceinline__ void sincos_small(float x, float &s, float &c)
-{
-    if (fabsf(x) <= 0.78539816f) {
-        const float z = x * x;
-        const float ps = fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
-        const float pc = fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f);
-        s = fmaf(x * z, ps, x);
-        c = fmaf(z * z, pc, fmaf(z, -0.5f, 1.0f));
-    } else {
-        sincosf(x, &s, &c);
-    }
+    const typename L::T r = L::rcp(den);
+    const typename L::T q = L::mul(num, r);
+    return L::fma(L::fma(L::neg(den), q, num), r, q);
 }
 
 // ---------------------------------------------------------------------------
@@ -65,7 +56,7 @@ struct CartPoleP {
     float pml_over_m;   // (masspole + length) / total_mass  -- PML is a SUM in the reference (:150-152)
     float gravity;      // :94
     float den_a;        // length * 4/3                                  (:426-428)
-    float den_b;        // length * masspole / total_mass
+    float neg_den_b;    // -(length * masspole / total_mass)
     float x_thr;        // largest float <= x_threshold: (v > x_thr) == (v > 2.4 in f64) for every float v
     float th_thr;       // same for theta_threshold_radians
     int semi_implicit;  // KinematicsIntegrator::Other (:437-441)
@@ -81,41 +72,78 @@ struct CartPole {
 
     __device__ __forceinline__ static bool valid(Action a) { return (uint32_t)a < 2u; }
 
-    // s = (x, x_dot, theta, theta_dot).  reward is decided by the caller (it depends on
-    // steps_beyond_terminated, :455-464).
-    __device__ __forceinline__ static void step(const P &p, float (&s)[SD], Action a,
-                                                float (&)[OD], float &reward, bool &done)
+    // force / M with the action's sign                                              :414-418
+    __device__ __forceinline__ static float pre(const P &p, Action a) { return (a == 1) ? p.force_over_m : -p.force_over_m; }
+
+    // A live CartPole has |theta| <= 0.21 (+ one step), so the common case needs neither range
+    // reduction nor quadrant selection; anything larger (a pole that keeps falling when the caller
+    // never resets) takes the full-range sincosf.
+    __device__ __forceinline__ static bool fast_ok(const P &, const float (&s)[SD]) { return fabsf(s[2]) <= 0.78539816f; }
+
+    // the equations of motion given sin / cos of the pole angle; s = (x, x_dot, theta, theta_dot)
+    template <class L>
+    __device__ __forceinline__ static void dynamics(const P &p, typename L::T (&s)[SD], typename L::T f,
+                                                    typename L::T sn, typename L::T cs)
     {
-        const float x = s[0], x_dot = s[1], theta = s[2], theta_dot = s[3];
-        const float f = (a == 1) ? p.force_over_m : -p.force_over_m; // :414-418, already / M
-        float sn, cs;
-        sincos_small(theta, sn, cs); // :420-421 (polynomial / sincosf, never the MUFU __sinf)
+        using T = typename L::T;
+        const T x = s[0], x_dot = s[1], theta = s[2], theta_dot = s[3];
         // temp = (force + PML * theta_dot^2 * sin) / M                               :423-424
-        const float temp = fmaf(p.pml_over_m * (theta_dot * theta_dot), sn, f);
+        const T temp = L::fma(L::mul(L::mul(theta_dot, theta_dot), L::bc(p.pml_over_m)), sn, f);
         // thetaacc = (g sin - cos temp) / (l (4/3 - mp cos^2 / M))                   :425-428
-        const float num = fmaf(p.gravity, sn, -(cs * temp));
-        const float den = fmaf(-p.den_b, cs * cs, p.den_a);
-        const float thetaacc = div_newton(num, den);
+        const T num = L::fma(L::bc(p.gravity), sn, L::neg(L::mul(cs, temp)));
+        const T den = L::fma(L::bc(p.neg_den_b), L::mul(cs, cs), L::bc(p.den_a));
+        const T thetaacc = div_newton<L>(num, den);
         // xacc = temp - PML thetaacc cos / M                                         :429
-        const float xacc = fmaf(-(p.pml_over_m * thetaacc), cs, temp);
-        float nx, nxd, nth, nthd;
+        const T xacc = L::fma(L::neg(L::mul(L::bc(p.pml_over_m), thetaacc)), cs, temp);
+        const T tau = L::bc(p.tau);
         if (!p.semi_implicit) { // Euler: positions use the OLD velocities          :431-436
-            nx = fmaf(p.tau, x_dot, x);
-            nxd = fmaf(p.tau, xacc, x_dot);
-            nth = fmaf(p.tau, theta_dot, theta);
-            nthd = fmaf(p.tau, thetaacc, theta_dot);
+            s[0] = L::fma(tau, x_dot, x);
+            s[1] = L::fma(tau, xacc, x_dot);
+            s[2] = L::fma(tau, theta_dot, theta);
+            s[3] = L::fma(tau, thetaacc, theta_dot);
         } else { //                                                                  :437-441
-            nxd = fmaf(p.tau, xacc, x_dot);
-            nx = fmaf(p.tau, nxd, x);
-            nthd = fmaf(p.tau, thetaacc, theta_dot);
-            nth = fmaf(p.tau, nthd, theta);
+            s[1] = L::fma(tau, xacc, x_dot);
+            s[0] = L::fma(tau, s[1], x);
+            s[3] = L::fma(tau, thetaacc, theta_dot);
+            s[2] = L::fma(tau, s[3], theta);
         }
-        s[0] = nx; s[1] = nxd; s[2] = nth; s[3] = nthd;
-        // strict comparisons on the updated x, theta                                 :450-453
-        // (x < -T || x > T) == (|x| > T).  The reference compares OrderedFloat values, a total
-        // order in which NaN is greater than everything, so a NaN state IS done: !(|x| <= T).
-        done = !(fabsf(nx) <= p.x_thr) | !(fabsf(nth) <= p.th_thr);
+    }
+
+    // fast path: |theta| <= pi/4 for every env of the lane                          :420-421
+    template <class L>
+    __device__ __forceinline__ static void advance(const P &p, typename L::T (&s)[SD], typename L::T f,
+                                                   typename L::T (&)[OD], typename L::T &reward)
+    {
+        typename L::T sn, cs;
+        sincos_poly<L>(s[2], sn, cs); // polynomial, never the MUFU __sinf
+        dynamics<L>(p, s, f, sn, cs);
+        reward = L::bc(1.0f); // decided by the caller beyond the first terminal step (:455-464)
+    }
+
+    __device__ __forceinline__ static void advance_slow(const P &p, float (&s)[SD], float f, float (&)[OD], float &reward)
+    {
+        float sn, cs;
+        sincosf(s[2], &sn, &cs);
+        dynamics<Lane1>(p, s, f, sn, cs);
         reward = 1.0f;
+    }
+
+    // strict comparisons on the updated x, theta                                     :450-453
+    // (x < -T || x > T) == (|x| > T).  The reference compares OrderedFloat values, a total
+    // order in which NaN is greater than everything, so a NaN state IS done: !(|x| <= T).
+    __device__ __forceinline__ static bool terminal(const P &p, const float (&s)[SD])
+    {
+        return !(fabsf(s[0]) <= p.x_thr) | !(fabsf(s[2]) <= p.th_thr);
+    }
+
+    // one env, scalar: the same bits as a Lane2 pair
+    __device__ __forceinline__ static void step(const P &p, float (&s)[SD], Action a,
+                                                float (&o)[OD], float &reward, bool &done)
+    {
+        const float f = pre(p, a);
+        if (fast_ok(p, s)) advance<Lane1>(p, s, f, o, reward);
+        else advance_slow(p, s, f, o, reward);
+        done = terminal(p, s);
     }
 
     // four iid uniforms in the order x, x_dot, theta, theta_dot                      :317-324
@@ -144,10 +172,10 @@ struct MountainCarP {
 // clip (util_fns.rs:2-10) on OrderedFloat values: in range -> value, greater than the right bound
 // -> right bound, else left bound.  OrderedFloat's total order puts NaN above everything, so a
 // NaN value is clipped to the RIGHT bound (fminf / fmaxf would return the left one).
+// fminf returns its non-NaN operand, so min-then-max is exactly that for every input (two FMNMX).
 __device__ __forceinline__ float clip_of(float v, float lo, float hi)
 {
-    v = !(v <= hi) ? hi : v;
-    return v < lo ? lo : v;
+    return fmaxf(fminf(v, hi), lo);
 }
 
 struct MountainCar {
@@ -159,21 +187,58 @@ struct MountainCar {
 
     __device__ __forceinline__ static bool valid(Action a) { return (uint32_t)a < 3u; }
 
-    __device__ __forceinline__ static void step(const P &p, float (&s)[SD], Action a,
-                                                float (&)[OD], float &reward, bool &done)
+    // (a - 1) * force                                                               :411
+    __device__ __forceinline__ static float pre(const P &p, Action a) { return __fmul_rn((float)(a - 1), p.force); }
+
+    // the position is clipped into [min_position, max_position] by every step, so 3 p stays tiny;
+    // a caller-injected far-out (or NaN) position takes the libm cosf
+    __device__ __forceinline__ static bool fast_ok(const P &, const float (&s)[SD]) { return fabsf(s[0]) <= TRIG_FAST_MAX / 4.0f; }
+
+    // everything after cos(3 p); s = (position, velocity)
+    template <class L>
+    __device__ __forceinline__ static void dynamics(const P &p, typename L::T (&s)[SD], typename L::T push, typename L::T c3p)
     {
-        float position = s[0], velocity = s[1];
-        // velocity += (a - 1) * force + cos(3 * position) * (-gravity)               :411-412
-        const float rhs = fmaf(cosf(3.0f * position), p.neg_gravity, (float)(a - 1) * p.force);
-        velocity += rhs;
-        velocity = clip_of(velocity, -p.max_speed, p.max_speed); //                  :413
-        position += velocity; //                                                      :415
-        position = clip_of(position, p.min_position, p.max_position); //              :416
+        using T = typename L::T;
+        // velocity += (a - 1) * force + cos(3 * position) * (-gravity): RHS first      :411-412
+        const T rhs = L::fma(c3p, L::bc(p.neg_gravity), push);
+        T velocity = L::fma(rhs, L::bc(1.0f), s[1]);
+        velocity = L::map(velocity, [&](float v, int) { return clip_of(v, -p.max_speed, p.max_speed); }); // :413
+        T position = L::fma(velocity, L::bc(1.0f), s[0]); //                              :415
+        position = L::map(position, [&](float v, int) { return clip_of(v, p.min_position, p.max_position); }); // :416
         // exact equality with the clipped wall value                                 :418-420
-        if (position == p.min_position && velocity < 0.0f) velocity = 0.0f;
-        done = (position >= p.goal_position) & (velocity >= p.goal_velocity); //      :422
-        reward = -1.0f; //                                                            :423
-        s[0] = position; s[1] = velocity;
+        velocity = L::map2(velocity, position, [&](float v, float x, int) { return (x == p.min_position && v < 0.0f) ? 0.0f : v; });
+        s[0] = position;
+        s[1] = velocity;
+    }
+
+    template <class L>
+    __device__ __forceinline__ static void advance(const P &p, typename L::T (&s)[SD], typename L::T push,
+                                                   typename L::T (&)[OD], typename L::T &reward)
+    {
+        typename L::T sn, cs;
+        sincos_reduced<L>(L::mul(s[0], L::bc(3.0f)), sn, cs);
+        dynamics<L>(p, s, push, cs);
+        reward = L::bc(-1.0f); //                                                     :423
+    }
+
+    __device__ __forceinline__ static void advance_slow(const P &p, float (&s)[SD], float push, float (&)[OD], float &reward)
+    {
+        dynamics<Lane1>(p, s, push, cosf(__fmul_rn(s[0], 3.0f)));
+        reward = -1.0f;
+    }
+
+    __device__ __forceinline__ static bool terminal(const P &p, const float (&s)[SD])
+    {
+        return (s[0] >= p.goal_position) & (s[1] >= p.goal_velocity); //              :422
+    }
+
+    __device__ __forceinline__ static void step(const P &p, float (&s)[SD], Action a,
+                                                float (&o)[OD], float &reward, bool &done)
+    {
+        const float push = pre(p, a);
+        if (fast_ok(p, s)) advance<Lane1>(p, s, push, o, reward);
+        else advance_slow(p, s, push, o, reward);
+        done = terminal(p, s);
     }
 
     __device__ __forceinline__ static void reset(const P &p, float (&s)[SD], float (&)[OD], uint4 w)
@@ -195,11 +260,12 @@ struct PendulumP {
 };
 
 // x - 2 pi * floor((x + pi) / (2 pi)) with a two-constant 2 pi (result in [-pi, pi) up to rounding)
-__device__ __forceinline__ float angle_normalize(float x)
+template <class L>
+__device__ __forceinline__ typename L::T angle_normalize(typename L::T x)
 {
-    const float k = floorf(fmaf(x, 0.15915494309189535f, 0.5f));
-    float r = fmaf(k, -6.2831854820251465f, x);   // 2 pi, high part (exact float)
-    return fmaf(k, 1.7484555e-07f, r);            // minus the low part (2pi_hi - 2pi)
+    const typename L::T k = L::floor(L::fma(x, L::bc(0.15915494309189535f), L::bc(0.5f)));
+    const typename L::T r = L::fma(k, L::bc(-6.2831854820251465f), x); // 2 pi, high part (exact float)
+    return L::fma(k, L::bc(1.7484555e-07f), r);                         // minus the low part (2pi_hi - 2pi)
 }
 
 struct Pendulum {
@@ -211,26 +277,61 @@ struct Pendulum {
 
     __device__ __forceinline__ static bool valid(Action) { return true; } // Box action: clipped, never rejected
 
+    // the clipped torque
+    __device__ __forceinline__ static float pre(const P &p, Action a) { return fminf(fmaxf(a, -p.max_torque), p.max_torque); }
+
+    // the stored angle is kept wrapped to [-pi, pi); a caller-injected far-out angle takes libm
+    __device__ __forceinline__ static bool fast_ok(const P &, const float (&s)[SD]) { return fabsf(s[0]) <= TRIG_FAST_MAX / 2.0f; }
+
+    // s = (theta, theta_dot), u = clipped torque, sin_th = sin(theta); o = (cos, sin, theta_dot) of the
+    // new state is filled by the caller from the returned new angle
+    template <class L>
+    __device__ __forceinline__ static void dynamics(const P &p, typename L::T (&s)[SD], typename L::T u,
+                                                    typename L::T sin_th, typename L::T &reward)
+    {
+        using T = typename L::T;
+        const T th = s[0], thdot = s[1];
+        const T an = angle_normalize<L>(th);
+        // cost uses the PRE-update theta, theta_dot and the clipped torque
+        const T costs = L::fma(an, an, L::fma(L::mul(thdot, L::bc(0.1f)), thdot, L::mul(L::mul(u, u), L::bc(0.001f))));
+        T newthdot = L::fma(L::fma(L::bc(p.c_sin), sin_th, L::mul(u, L::bc(p.c_u))), L::bc(p.dt), thdot);
+        newthdot = L::map(newthdot, [&](float v, int) { return fminf(fmaxf(v, -p.max_speed), p.max_speed); });
+        // uses the clipped NEW velocity.  Stored theta is kept wrapped to [-pi, pi): observation and
+        // cost are invariant under the wrap, and f32 cos/sin stay accurate on arbitrarily long spins
+        // (inside the range the wrap is the identity: k = 0).
+        s[0] = angle_normalize<L>(L::fma(newthdot, L::bc(p.dt), th));
+        s[1] = newthdot;
+        reward = L::neg(costs);
+    }
+
+    template <class L>
+    __device__ __forceinline__ static void advance(const P &p, typename L::T (&s)[SD], typename L::T u,
+                                                   typename L::T (&o)[OD], typename L::T &reward)
+    {
+        typename L::T sn, cs;
+        sincos_reduced<L>(s[0], sn, cs);
+        dynamics<L>(p, s, u, sn, reward);
+        sincos_reduced<L>(s[0], sn, cs); // |new theta| <= pi
+        o[0] = cs; o[1] = sn; o[2] = s[1];
+    }
+
+    __device__ __forceinline__ static void advance_slow(const P &p, float (&s)[SD], float u, float (&o)[OD], float &reward)
+    {
+        dynamics<Lane1>(p, s, u, sinf(s[0]), reward);
+        float sn, cs;
+        sincos_reduced<Lane1>(s[0], sn, cs);
+        o[0] = cs; o[1] = sn; o[2] = s[1];
+    }
+
+    __device__ __forceinline__ static bool terminal(const P &, const float (&)[SD]) { return false; } // never terminates
+
     __device__ __forceinline__ static void step(const P &p, float (&s)[SD], Action a,
                                                 float (&o)[OD], float &reward, bool &done)
     {
-        const float th = s[0], thdot = s[1];
-        const float u = fminf(fmaxf(a, -p.max_torque), p.max_torque);
-        const float an = angle_normalize(th);
-        // cost uses the PRE-update theta, theta_dot and the clipped torque
-        const float costs = fmaf(an, an, fmaf(0.1f * thdot, thdot, 0.001f * (u * u)));
-        float newthdot = fmaf(fmaf(p.c_sin, sinf(th), p.c_u * u), p.dt, thdot);
-        newthdot = fminf(fmaxf(newthdot, -p.max_speed), p.max_speed);
-        float newth = fmaf(newthdot, p.dt, th); // uses the clipped NEW velocity
-        // Stored theta is kept wrapped to [-pi, pi): observation and cost are invariant under
-        // the wrap, and f32 cos/sin stay accurate on arbitrarily long spins.
-        if (fabsf(newth) > 3.14159274f) newth = angle_normalize(newth);
-        float sn, cs;
-        sincosf(newth, &sn, &cs);
-        s[0] = newth; s[1] = newthdot;
-        o[0] = cs; o[1] = sn; o[2] = newthdot;
-        reward = -costs;
-        done = false; // never terminates
+        const float u = pre(p, a);
+        if (fast_ok(p, s)) advance<Lane1>(p, s, u, o, reward);
+        else advance_slow(p, s, u, o, reward);
+        done = false;
     }
 
     __device__ __forceinline__ static void reset(const P &p, float (&s)[SD], float (&o)[OD], uint4 w)

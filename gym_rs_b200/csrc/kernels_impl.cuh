@@ -30,6 +30,11 @@ namespace gymrs {
 
 namespace {
 
+// Env index inside one launch.  A handle holds at most 2^31 envs (gymrs_create), so 32 bits do:
+// one register instead of two per index, and one IMAD / LEA less per address.  Global ids (the
+// Philox counter) stay 64-bit: global_off + index.
+using idx_t = uint32_t;
+
 // ---- programmatic dependent launch (PDL) ----------------------------------
 // wait: block until the previous grid in the stream has completed and its writes are visible.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -172,74 +177,219 @@ __device__ __forceinline__ void advance_epoch(const BatchArgs &a, uint64_t first
 }
 
 // ---- one transition of the V envs a thread owns, all on registers ------------
-template <class E, int V, bool AR, bool SBT, bool TL>
-__device__ __forceinline__ void transition(const typename E::P &p, const BatchArgs &a,
-                                           float (&s)[E::SD][V], float (&o)[E::OD][V],
-                                           const typename E::Action (&act)[V],
-                                           int32_t (&sbt)[V], uint32_t (&el)[V],
-                                           float (&rew)[V], uint8_t (&dn)[V], uint8_t (&tr)[V],
-                                           uint64_t gid0, uint64_t epoch, int nvalid)
+#ifndef GYMRS_FAST_LANE
+#define GYMRS_FAST_LANE 2 // 2: packed pairs (Lane2); 1: the same straight-line path on scalar lanes (A/B builds)
+#endif
+
+// Straight-line condition: every env of this thread has a valid action and a state inside the range
+// of the branch-free trig.  Always true for envs that are reset when they end (a live CartPole has
+// |theta| <= 0.21, a MountainCar position is clipped, a Pendulum angle is stored wrapped).
+template <class E, int V>
+__device__ __forceinline__ bool all_fast(const typename E::P &p, const float (&s)[E::SD][V], const typename E::Action (&act)[V])
 {
-    uint32_t need_reset = 0; // bit j: env j of this thread ended its episode in this step
+    bool fast = true;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-        float sj[E::SD], oj[E::OD];
+        float sj[E::SD];
 #pragma unroll
         for (int r = 0; r < E::SD; ++r) sj[r] = s[r][j];
-#pragma unroll
-        for (int r = 0; r < E::OD; ++r) oj[r] = o[r][j];
-        float reward = 0.0f;
-        bool done = false, trunc = false;
-        if (E::valid(act[j])) {
-            E::step(p, sj, act[j], oj, reward, done);
-            if (SBT && E::HAS_SBT) {
-                // reward 1.0 while alive and on the FIRST terminal step, 0.0 afterwards
-                // (cartpole.rs:455-464); the state keeps integrating.
-                if (done) {
-                    if (sbt[j] < 0) { sbt[j] = 0; }
-                    else { sbt[j] += 1; reward = 0.0f; }
-                }
-            }
-            if (TL) {
-                el[j] += 1u;
-                trunc = el[j] >= a.max_steps;
-            }
-            if (AR && (done || trunc)) need_reset |= 1u << j;
-        } else if (j < nvalid) {
-            report_invalid(a.err, gid0 + j, (uint32_t)act[j]); //          cartpole.rs:402-406
-        }
-#pragma unroll
-        for (int r = 0; r < E::SD; ++r) s[r][j] = sj[r];
-#pragma unroll
-        for (int r = 0; r < E::OD; ++r) o[r][j] = oj[r];
-        rew[j] = reward;
-        dn[j] = done ? 1 : 0;
-        tr[j] = trunc ? 1 : 0;
+        fast = fast & E::valid(act[j]) & E::fast_ok(p, sj);
     }
-    if (AR) {
-        // Same-launch auto-reset (examples/cartpole.rs:23-28 does it by hand).  Only a few percent
-        // of envs end per step, so instead of a predicated Philox per slot (which nearly every warp
-        // would execute V times) each thread draws once per finished env: the loop runs as often as
-        // the busiest lane of the warp needs, typically once.
-        while (need_reset) {
-            const int j = __ffs(need_reset) - 1;
-            need_reset &= need_reset - 1;
+    return fast;
+}
+
+// The dynamics of V envs on the straight-line path, two at a time on packed fp32 (Lane2: FFMA2 /
+// FMUL2, one issue slot per two FMAs).
+template <class E, int V>
+__device__ __forceinline__ void advance_fast(const typename E::P &p, float (&s)[E::SD][V], float (&o)[E::OD][V],
+                                             const typename E::Action (&act)[V], float (&rew)[V])
+{
+    static_assert(V % 2 == 0, "pairs");
+    if constexpr (GYMRS_FAST_LANE == 1) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
             float sj[E::SD], oj[E::OD];
-            E::reset(p, sj, oj, reset_words(a.rk, gid0 + j, epoch));
 #pragma unroll
-            for (int jj = 0; jj < V; ++jj) {
-                if (jj == j) {
+            for (int r = 0; r < E::SD; ++r) sj[r] = s[r][j];
+            E::template advance<Lane1>(p, sj, E::pre(p, act[j]), oj, rew[j]);
 #pragma unroll
-                    for (int r = 0; r < E::SD; ++r) s[r][jj] = sj[r];
-                    if (!E::OBS_IS_STATE) {
+            for (int r = 0; r < E::SD; ++r) s[r][j] = sj[r];
+            if (!E::OBS_IS_STATE) {
 #pragma unroll
-                        for (int r = 0; r < E::OD; ++r) o[r][jj] = oj[r];
-                    }
-                    if (SBT) sbt[jj] = -1; //                              cartpole.rs:504
-                    if (TL) el[jj] = 0u;
-                }
+                for (int r = 0; r < E::OD; ++r) o[r][j] = oj[r];
             }
         }
+    } else {
+#pragma unroll
+        for (int q = 0; q < V / 2; ++q) {
+            typename Lane2::T ps[E::SD], po[E::OD], pr;
+#pragma unroll
+            for (int r = 0; r < E::SD; ++r) ps[r] = Lane2::pack(s[r][2 * q], s[r][2 * q + 1]);
+            E::template advance<Lane2>(p, ps, Lane2::pack(E::pre(p, act[2 * q]), E::pre(p, act[2 * q + 1])), po, pr);
+#pragma unroll
+            for (int r = 0; r < E::SD; ++r) Lane2::unpack(ps[r], s[r][2 * q], s[r][2 * q + 1]);
+            if (!E::OBS_IS_STATE) {
+#pragma unroll
+                for (int r = 0; r < E::OD; ++r) Lane2::unpack(po[r], o[r][2 * q], o[r][2 * q + 1]);
+            }
+            Lane2::unpack(pr, rew[2 * q], rew[2 * q + 1]);
+        }
+    }
+}
+
+// Per-env bookkeeping after the dynamics: reward beyond termination, time limit, flags.
+// Returns true when the env ended its episode in this step (done or truncated).
+template <class E, bool SBT, bool TL>
+__device__ __forceinline__ bool settle(const BatchArgs &a, float reward, bool done, int32_t &sbt, uint32_t &el,
+                                       float &rew, uint8_t &dn, uint8_t &tr)
+{
+    bool trunc = false;
+    if (SBT && E::HAS_SBT) {
+        // reward 1.0 while alive and on the FIRST terminal step, 0.0 afterwards
+        // (cartpole.rs:455-464); the state keeps integrating.
+        if (done) {
+            if (sbt < 0) { sbt = 0; }
+            else { sbt += 1; reward = 0.0f; }
+        }
+    }
+    if (TL) {
+        el += 1u;
+        trunc = el >= a.max_steps;
+    }
+    rew = reward;
+    dn = done ? 1 : 0;
+    tr = trunc ? 1 : 0;
+    return done | trunc;
+}
+
+// The rare per-env path of a fused rollout (full-range libm trig for a far-out angle or position),
+// out of line so that its ~100-instruction range reduction does not sit inside every env slot.
+template <class E>
+__device__ __noinline__ void step_out_of_line(const typename E::P &p, float (&s)[E::SD], typename E::Action a,
+                                              float (&o)[E::OD], float &reward, bool &done)
+{
+    E::step(p, s, a, o, reward, done);
+}
+
+// One transition of the V envs held in registers.  Finished envs are NOT re-sampled here; the mask
+// of them (bit j, only j < nvalid) is returned: a step overwrites them after its row stores
+// (reset_patch), a rollout merges fresh states into its registers (reset_merge).
+// ASSUME_FAST: the caller has already established all_fast().
+template <class E, int V, bool AR, bool SBT, bool TL, bool ASSUME_FAST = false>
+__device__ __forceinline__ uint32_t transition(const typename E::P &p, const BatchArgs &a,
+                                               float (&s)[E::SD][V], float (&o)[E::OD][V],
+                                               const typename E::Action (&act)[V],
+                                               int32_t (&sbt)[V], uint32_t (&el)[V],
+                                               float (&rew)[V], uint8_t (&dn)[V], uint8_t (&tr)[V],
+                                               uint64_t gid0, int nvalid)
+{
+    uint32_t ended = 0;
+    bool fast = false;
+    if constexpr (V % 2 == 0) fast = ASSUME_FAST || all_fast<E, V>(p, s, act);
+    if (fast) {
+        if constexpr (V % 2 == 0) {
+            advance_fast<E, V>(p, s, o, act, rew);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float sj[E::SD];
+#pragma unroll
+                for (int r = 0; r < E::SD; ++r) sj[r] = s[r][j];
+                if (settle<E, SBT, TL>(a, rew[j], E::terminal(p, sj), sbt[j], el[j], rew[j], dn[j], tr[j])) ended |= 1u << j;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float sj[E::SD], oj[E::OD];
+#pragma unroll
+            for (int r = 0; r < E::SD; ++r) sj[r] = s[r][j];
+#pragma unroll
+            for (int r = 0; r < E::OD; ++r) oj[r] = o[r][j];
+            float reward = 0.0f;
+            bool done = false;
+            if (E::valid(act[j])) {
+                if (V % 2 == 0) step_out_of_line<E>(p, sj, act[j], oj, reward, done);
+                else E::step(p, sj, act[j], oj, reward, done);
+                if (settle<E, SBT, TL>(a, reward, done, sbt[j], el[j], rew[j], dn[j], tr[j])) ended |= 1u << j;
+            } else {
+                if (j < nvalid) report_invalid(a.err, gid0 + j, (uint32_t)act[j]); //   cartpole.rs:402-406
+                rew[j] = 0.0f;
+                dn[j] = 0;
+                tr[j] = 0;
+            }
+#pragma unroll
+            for (int r = 0; r < E::SD; ++r) s[r][j] = sj[r];
+#pragma unroll
+            for (int r = 0; r < E::OD; ++r) o[r][j] = oj[r];
+        }
+    }
+    return AR ? (ended & ((1u << nvalid) - 1u)) : 0u;
+}
+
+// Same-launch auto-reset (examples/cartpole.rs:23-28 does it by hand).  Only a few percent of envs
+// end per step, so instead of a predicated Philox per slot (which nearly every warp would execute V
+// times) each thread draws once per finished env: the loop runs as often as the busiest lane of the
+// warp needs, typically once.
+//
+// reset_merge: the fresh state goes into the registers (fused rollout: the envs keep stepping).
+template <class E, int V, bool SBT, bool TL>
+__device__ __forceinline__ void reset_merge(const typename E::P &p, const BatchArgs &a, float (&s)[E::SD][V],
+                                            float (&o)[E::OD][V], int32_t (&sbt)[V], uint32_t (&el)[V],
+                                            uint64_t gid0, uint64_t epoch, uint32_t ended)
+{
+    while (ended) {
+        const int j = __ffs(ended) - 1;
+        ended &= ended - 1;
+        float sj[E::SD], oj[E::OD];
+        E::reset(p, sj, oj, reset_words(a.rk, gid0 + j, epoch));
+#pragma unroll
+        for (int jj = 0; jj < V; ++jj) {
+            if (jj == j) {
+#pragma unroll
+                for (int r = 0; r < E::SD; ++r) s[r][jj] = sj[r];
+                if (!E::OBS_IS_STATE) {
+#pragma unroll
+                    for (int r = 0; r < E::OD; ++r) o[r][jj] = oj[r];
+                }
+                if (SBT) sbt[jj] = -1; //                              cartpole.rs:504
+                if (TL) el[jj] = 0u;
+            }
+        }
+    }
+}
+
+// reset_patch: a single step stores its rows first and then overwrites each finished env i0 + j with
+// its fresh state (same thread, same address: program order).  The state does not have to stay live
+// across the Philox evaluation (fewer registers) and the row stores are issued before it; the lines
+// are still in L2, so the 4-byte stores cost no extra DRAM traffic.
+// FROM_THREAD: i0 = (blockIdx.x * blockDim.x + threadIdx.x) * V is re-derived from the special
+// registers inside the loop (volatile, so that it is not merged with the first evaluation) rather
+// than kept live across the row stores -- at 48 registers ptxas would otherwise spill it.
+template <class E, bool SBT, bool TL, int FROM_THREAD = 0>
+__device__ __forceinline__ void reset_patch(const typename E::P &p, const BatchArgs &a, idx_t i0, uint64_t epoch,
+                                            uint32_t ended)
+{
+    while (ended) {
+        const int j = __ffs(ended) - 1;
+        ended &= ended - 1;
+        if (FROM_THREAD) {
+            uint32_t t, c, n;
+            asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+            asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(c));
+            asm volatile("mov.u32 %0, %%ntid.x;" : "=r"(n));
+            i0 = (c * n + t) * (idx_t)FROM_THREAD;
+        }
+        float sj[E::SD], oj[E::OD];
+        const idx_t i = i0 + (idx_t)j;
+        E::reset(p, sj, oj, reset_words(a.rk, a.global_off + i, epoch));
+#pragma unroll
+        for (int r = 0; r < E::SD; ++r) a.state[r * a.ld + i] = sj[r];
+        if (!E::OBS_IS_STATE) {
+#pragma unroll
+            for (int r = 0; r < E::OD; ++r) a.obs[r * a.ld + i] = oj[r];
+        }
+        if (SBT) a.sbt[i] = -1; //                                          cartpole.rs:504
+        if (TL) a.elapsed[i] = 0u;
     }
 }
 
@@ -248,22 +398,12 @@ __device__ __forceinline__ void transition(const typename E::P &p, const BatchAr
 #define GYMRS_STEP_MIN_CTAS 5 // <= 51 registers/thread: 5 CTAs of 256 threads resident per SM
 #endif
 
-template <class E, int V, bool AR, bool SBT, bool TL, bool FULL>
-__device__ __forceinline__ void step_body(const typename E::P &p, const BatchArgs &a, uint64_t i0,
-                                          int nvalid, typename E::Action (&act)[V], uint64_t epoch)
+// store the results of V envs (rows of the handle's SoA arrays)
+template <class E, int V, bool SBT, bool TL, bool FULL>
+__device__ __forceinline__ void store_rows(const BatchArgs &a, idx_t i0, int nvalid, const float (&s)[E::SD][V],
+                                           const float (&o)[E::OD][V], const int32_t (&sbt)[V], const uint32_t (&el)[V],
+                                           const float (&rew)[V], const uint8_t (&dn)[V], const uint8_t (&tr)[V])
 {
-    float s[E::SD][V], o[E::OD][V];
-#pragma unroll
-    for (int r = 0; r < E::SD; ++r) ld_row<V, FULL>(a.state + r * a.ld + i0, s[r], nvalid, 0.0f);
-    int32_t sbt[V];
-    uint32_t el[V];
-    if (SBT) ld_row<V, FULL>(a.sbt + i0, sbt, nvalid, int32_t(-1));
-    if (TL) ld_row<V, FULL>(a.elapsed + i0, el, nvalid, uint32_t(0));
-
-    float rew[V];
-    uint8_t dn[V], tr[V];
-    transition<E, V, AR, SBT, TL>(p, a, s, o, act, sbt, el, rew, dn, tr, a.global_off + i0, epoch, nvalid);
-
 #pragma unroll
     for (int r = 0; r < E::SD; ++r) st_row<V, FULL>(a.state + r * a.ld + i0, s[r], nvalid);
     if (!E::OBS_IS_STATE) {
@@ -277,15 +417,81 @@ __device__ __forceinline__ void step_body(const typename E::P &p, const BatchArg
     if (TL) st_row<V, FULL>(a.elapsed + i0, el, nvalid);
 }
 
+// One env at a time, everything from and to global memory, scalar lanes: the general form of a step
+// (any action, any state, any alignment).  The V = 1 kernels run it inline; the vector kernels call
+// the out-of-line copy below for the rare thread that cannot take the straight-line path and for the
+// ragged tail of a batch, so that none of this shapes the hot path's registers.
+template <class E, bool AR, bool SBT, bool TL>
+__device__ __forceinline__ void step_env_scalar(const typename E::P &p, const BatchArgs &a, idx_t i, uint64_t epoch)
+{
+    using A = typename E::Action;
+    A act[1] = {__ldg(reinterpret_cast<const A *>(a.actions) + i)};
+    float s[E::SD][1], o[E::OD][1];
+#pragma unroll
+    for (int r = 0; r < E::SD; ++r) s[r][0] = __ldcg(a.state + r * a.ld + i);
+    int32_t sbt[1] = {-1};
+    uint32_t el[1] = {0u};
+    if (SBT) sbt[0] = __ldcg(a.sbt + i);
+    if (TL) el[0] = __ldcg(a.elapsed + i);
+    float rew[1];
+    uint8_t dn[1], tr[1];
+    const uint32_t ended = transition<E, 1, AR, SBT, TL>(p, a, s, o, act, sbt, el, rew, dn, tr, a.global_off + i, 1);
+    store_rows<E, 1, SBT, TL, true>(a, i, 1, s, o, sbt, el, rew, dn, tr);
+    if (AR) reset_patch<E, SBT, TL>(p, a, i, epoch, ended);
+}
+
+template <class E, bool AR, bool SBT, bool TL>
+__device__ __noinline__ void step_envs_out_of_line(const typename E::P &p, const BatchArgs &a, idx_t i0, int count,
+                                                   uint64_t epoch)
+{
+    for (int j = 0; j < count; ++j) step_env_scalar<E, AR, SBT, TL>(p, a, i0 + j, epoch);
+}
+
+template <class E, int V, bool AR, bool SBT, bool TL, bool FULL>
+__device__ __forceinline__ void step_body(const typename E::P &p, const BatchArgs &a, idx_t i0,
+                                          int nvalid, typename E::Action (&act)[V], uint64_t epoch)
+{
+    if constexpr (V == 1) {
+        step_env_scalar<E, AR, SBT, TL>(p, a, i0, epoch);
+    } else if constexpr (!FULL) {
+        step_envs_out_of_line<E, AR, SBT, TL>(p, a, i0, nvalid, epoch); // the one ragged group at the end of a batch
+    } else {
+        float s[E::SD][V], o[E::OD][V];
+#pragma unroll
+        for (int r = 0; r < E::SD; ++r) ld_row<V, true>(a.state + r * a.ld + i0, s[r], V, 0.0f);
+        int32_t sbt[V];
+        uint32_t el[V];
+        if (SBT) ld_row<V, true>(a.sbt + i0, sbt, V, int32_t(-1));
+        if (TL) ld_row<V, true>(a.elapsed + i0, el, V, uint32_t(0));
+        if (!all_fast<E, V>(p, s, act)) {
+            step_envs_out_of_line<E, AR, SBT, TL>(p, a, i0, V, epoch);
+            return;
+        }
+        float rew[V];
+        uint8_t dn[V], tr[V];
+        const uint32_t ended = transition<E, V, AR, SBT, TL, true>(p, a, s, o, act, sbt, el, rew, dn, tr, a.global_off + i0, V);
+#ifndef GYMRS_RESET_PATCH
+// 0 (default): fresh states are merged into the registers before the row stores.  1: the rows are stored
+// first and finished envs overwritten afterwards (reset_patch) -- measured slower: the scattered 4-byte
+// stores cost more than they save once the state is L2-resident (profiles/r02_sweeps.md).
+#define GYMRS_RESET_PATCH 0
+#endif
+        if (AR && !GYMRS_RESET_PATCH) reset_merge<E, V, SBT, TL>(p, a, s, o, sbt, el, a.global_off + i0, epoch, ended);
+        store_rows<E, V, SBT, TL, true>(a, i0, V, s, o, sbt, el, rew, dn, tr);
+        if (AR && GYMRS_RESET_PATCH) reset_patch<E, SBT, TL, V>(p, a, 0, epoch, ended);
+    }
+}
+
 template <class E, int V, bool AR, bool SBT, bool TL, bool DEVC>
 __global__ void __launch_bounds__(256, GYMRS_STEP_MIN_CTAS)
 step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ BatchArgs a)
 {
     using A = typename E::Action;
-    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
-    const bool live = i0 < a.n;
-    const bool full = i0 + V <= a.n;
-    const int nvalid = live ? (full ? V : (int)(a.n - i0)) : 0;
+    const idx_t n = (idx_t)a.n;
+    const idx_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * V; // < 2^31 + 1024: no wrap
+    const bool live = i0 < n;
+    const bool full = live && n - i0 >= (idx_t)V;
+    const int nvalid = live ? (full ? V : (int)(n - i0)) : 0;
     const A *actp = reinterpret_cast<const A *>(a.actions) + i0;
 
     // Before any dependency is resolved: pull this CTA's input rows into L2 with one bulk prefetch
@@ -294,9 +500,9 @@ step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Bat
     // of launch t + 1 overlap the tail of launch t even when the launch has to wait for the whole
     // previous grid (pdl = 1): after the wait the row loads are L2 hits.
     if (a.l2_prefetch && threadIdx.x <= E::SD) {
-        const uint64_t cta0 = (uint64_t)blockIdx.x * blockDim.x * V;
-        if (cta0 < a.n) {
-            const uint64_t left = a.n - cta0, span = (uint64_t)blockDim.x * V;
+        const idx_t cta0 = blockIdx.x * blockDim.x * V;
+        if (cta0 < n) {
+            const idx_t left = n - cta0, span = blockDim.x * V;
             const uint32_t bytes = (uint32_t)((left < span ? left : span) * 4u) & ~15u;
             const void *src = threadIdx.x < E::SD
                                   ? static_cast<const void *>(a.state + threadIdx.x * a.ld + cta0)
@@ -309,10 +515,8 @@ step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Bat
     A act[V];
     // pdl == 2: the caller guarantees the action batch predates the previous launch, so it can
     // be fetched before any dependency is resolved
-    if (a.early_actions) {
-        if (full) ld_stream<V, true>(actp, act, nvalid);
-        else if (live) ld_stream<V, false>(actp, act, nvalid);
-    }
+    // (the scalar forms -- V = 1, the ragged group at the end -- fetch their own actions)
+    if (V > 1 && a.early_actions && full) ld_stream<V, true>(actp, act, nvalid);
 
     // let the next launch in the stream get its CTAs scheduled as soon as SM slots free up
     pdl_launch_dependents();
@@ -342,10 +546,7 @@ step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ Bat
 
     const uint64_t epoch = first_epoch<DEVC>(a);
     if (live) {
-        if (!a.early_actions) {
-            if (full) ld_stream<V, true>(actp, act, nvalid);
-            else ld_stream<V, false>(actp, act, nvalid);
-        }
+        if (V > 1 && !a.early_actions && full) ld_stream<V, true>(actp, act, nvalid);
         if (full) step_body<E, V, AR, SBT, TL, true>(p, a, i0, nvalid, act, epoch);
         else step_body<E, V, AR, SBT, TL, false>(p, a, i0, nvalid, act, epoch);
     }
@@ -542,7 +743,7 @@ step_stream_kernel(const __grid_constant__ typename E::P p, const __grid_constan
         const uint64_t t = tile_of(k);
         mbar_wait(&full[st], (k / S) & 1u);
         if (il < tile_envs(t)) {
-            const uint64_t i0 = t * TMA_TILE + il;
+            const idx_t i0 = (idx_t)t * TMA_TILE + il;
             float s[E::SD][V], o[E::OD][V];
             A act[V];
             int32_t sbt[V];
@@ -553,20 +754,16 @@ step_stream_kernel(const __grid_constant__ typename E::P p, const __grid_constan
             if (SBT) unpack<V>(*reinterpret_cast<const int4 *>(&tile[st][R_SBT][il]), sbt);
             if (TL) unpack<V>(*reinterpret_cast<const uint4 *>(&tile[st][R_EL][il]), el);
 
-            float rew[V];
-            uint8_t dn[V], tr[V];
-            transition<E, V, AR, SBT, TL>(p, a, s, o, act, sbt, el, rew, dn, tr, a.global_off + i0, a.epoch, V);
-#pragma unroll
-            for (int r = 0; r < E::SD; ++r) st_row<V, true>(a.state + r * a.ld + i0, s[r], V);
-            if (!E::OBS_IS_STATE) {
-#pragma unroll
-                for (int r = 0; r < E::OD; ++r) st_row<V, true>(a.obs + r * a.ld + i0, o[r], V);
+            if (!all_fast<E, V>(p, s, act)) {
+                step_envs_out_of_line<E, AR, SBT, TL>(p, a, i0, V, a.epoch); // re-reads this thread's envs from global
+            } else {
+                float rew[V];
+                uint8_t dn[V], tr[V];
+                const uint32_t ended = transition<E, V, AR, SBT, TL, true>(p, a, s, o, act, sbt, el, rew, dn, tr,
+                                                                               a.global_off + i0, V);
+                store_rows<E, V, SBT, TL, true>(a, i0, V, s, o, sbt, el, rew, dn, tr);
+                if (AR) reset_patch<E, SBT, TL>(p, a, i0, a.epoch, ended);
             }
-            st_row<V, true>(a.reward + i0, rew, V);
-            st_row<V, true>(a.done + i0, dn, V);
-            if (TL) st_row<V, true>(a.truncated + i0, tr, V);
-            if (SBT) st_row<V, true>(a.sbt + i0, sbt, V);
-            if (TL) st_row<V, true>(a.elapsed + i0, el, V);
         }
         mbar_arrive(&done[st]); // this thread has read the stage and issued its stores for tile k
     }
@@ -577,7 +774,7 @@ step_stream_kernel(const __grid_constant__ typename E::P p, const __grid_constan
 // reads one action row and streams out observation / reward / done.  The actions of
 // step k+1 are loaded before the math of step k so their latency is covered.
 template <class E, int V, bool AR, bool SBT, bool TL, bool FULL>
-__device__ __forceinline__ void rollout_body(const typename E::P &p, const BatchArgs &a, uint64_t i0, int nvalid,
+__device__ __forceinline__ void rollout_body(const typename E::P &p, const BatchArgs &a, idx_t i0, int nvalid,
                                              uint64_t epoch)
 {
     using A = typename E::Action;
@@ -597,8 +794,8 @@ __device__ __forceinline__ void rollout_body(const typename E::P &p, const Batch
 
     for (uint32_t k = 0; k < a.n_steps; ++k) {
         if (k + 1 < a.n_steps) ld_stream<V, FULL>(actp + (uint64_t)(k + 1) * a.act_ld, act_next, nvalid);
-        transition<E, V, AR, SBT, TL>(p, a, s, o, act, sbt, el, rew, dn, tr, a.global_off + i0,
-                                      epoch + k, nvalid);
+        const uint32_t ended = transition<E, V, AR, SBT, TL>(p, a, s, o, act, sbt, el, rew, dn, tr, a.global_off + i0, nvalid);
+        if (AR) reset_merge<E, V, SBT, TL>(p, a, s, o, sbt, el, a.global_off + i0, epoch + k, ended);
         if (a.obs_out) {
             float *ob = a.obs_out + (uint64_t)k * E::OD * a.out_ld + i0;
 #pragma unroll
@@ -630,10 +827,11 @@ template <class E, int V, bool AR, bool SBT, bool TL, bool DEVC>
 __global__ void __launch_bounds__(256)
 rollout_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ BatchArgs a)
 {
-    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    const idx_t n = (idx_t)a.n;
+    const idx_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * V;
     const uint64_t epoch = first_epoch<DEVC>(a);
-    if (i0 + V <= a.n) rollout_body<E, V, AR, SBT, TL, true>(p, a, i0, V, epoch);
-    else if (i0 < a.n) rollout_body<E, V, AR, SBT, TL, false>(p, a, i0, (int)(a.n - i0), epoch);
+    if (i0 < n && n - i0 >= (idx_t)V) rollout_body<E, V, AR, SBT, TL, true>(p, a, i0, V, epoch);
+    else if (i0 < n) rollout_body<E, V, AR, SBT, TL, false>(p, a, i0, (int)(n - i0), epoch);
     advance_epoch<DEVC>(a, epoch, a.n_steps);
 }
 
