@@ -8,6 +8,8 @@ writes profiles/<round>_launches_<env>.csv        (per-kernel totals of the laun
        profiles/<round>_ncu_<env>.json            (key metrics of each --set full capture)
        profiles/<round>_steady_dram_<env>.json    (single-pass dram bytes, --cache-control none)
        profiles/roofline_traffic.json             (bytes per launch that bench.py reports as `traffic`)
+       profiles/kernel_isolated.json              (avg duration, us, of ONE isolated step-kernel launch per env,
+                                                   from the launch list: what bench.py reports as `kernel_us_isolated`)
 """
 import collections
 import csv
@@ -84,11 +86,18 @@ def main():
     tp = os.path.join(PROF, "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp))
+    isolated = {}
+    ip = os.path.join(PROF, "kernel_isolated.json")
+    if os.path.exists(ip):
+        isolated = json.load(open(ip))
     for env in ENVS:
         lp = os.path.join(OUT, f"launches_{env}.csv")
         if os.path.exists(lp):
             agg = launches(lp)
             total = sum(t for _, t in agg.values())
+            steps = [(c, t) for k, (c, t) in agg.items() if "step_kernel" in k]
+            if steps:
+                isolated[env] = sum(t for _, t in steps) / sum(c for c, _ in steps)
             with open(os.path.join(PROF, f"{rnd}_launches_{env}.csv"), "w") as f:
                 f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised launches)\n")
                 f.write("launches,total_us,avg_us,share,kernel\n")
@@ -117,8 +126,13 @@ def main():
                                 "is the steady-state DRAM traffic")
                 json.dump(summ, open(os.path.join(PROF, f"{rnd}_steady_dram_{env}.json"), "w"), indent=1)
                 traffic[env] = summ["dram__bytes_read.sum"] + summ["dram__bytes_write.sum"]
+    rep = os.path.join(OUT, "prof_rollout_cartpole.ncu-rep")
+    if os.path.exists(rep):
+        json.dump(raw_page(rep), open(os.path.join(PROF, f"{rnd}_ncu_rollout_cartpole.json"), "w"), indent=1)
     json.dump(traffic, open(tp, "w"), indent=1)
+    json.dump(isolated, open(ip, "w"), indent=1)
     print("roofline traffic (bytes per launch):", traffic)
+    print("isolated step-kernel launch (us):", isolated)
 
 
 if __name__ == "__main__":
