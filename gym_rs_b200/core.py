@@ -102,6 +102,7 @@ class Env(EnvProperties):
     ACTION_DTYPE = "int32"
     INFO_ON_STEP = None        # cartpole: Some(()) -> (); mountain car: None
     INVALID_FMT = "{} usize invalid"
+    WARNS_AFTER_TERMINATION = False  # CartPole logs a warning when stepped after termination (cartpole.rs:461)
     _METADATA = Metadata((), 0)
 
     def __init__(self, render_mode: RenderMode = RenderMode.NONE, num_envs: int = 1, device: int = 0,
@@ -261,6 +262,11 @@ class Env(EnvProperties):
             if rc == _capi.ERR_INVALID_ACTION:
                 raise AssertionError(self.INVALID_FMT.format(action))  # cartpole.rs:402-406
             _capi.check(rc)
+            if self.WARNS_AFTER_TERMINATION and dn[0] and rew[0] == 0.0:
+                # reward 0 on a terminal step: the env had terminated before this call (cartpole.rs:455-464)
+                import logging
+                logging.getLogger("gym_rs").warning(
+                    "Calling step after termination may result in undefined behaviour. Consider reseting.")
             return ActionReward(self.OBSERVATION(*[float(v) for v in obs[:, 0]]), float(rew[0]),
                                 bool(dn[0]), bool(tr[0]), self.INFO_ON_STEP)
         # A 1 M-env step is ~6 us of GPU time, so the host side of this call matters: the checks

@@ -37,6 +37,7 @@ class CartPoleEnv(Env):
     KIND = _capi.CARTPOLE
     OBSERVATION = CartPoleObservation
     STATE = CartPoleObservation
+    WARNS_AFTER_TERMINATION = True
     ACTION_DTYPE = "int32"
     INFO_ON_STEP = ()                    # info: Some(()), cartpole.rs:481
     INVALID_FMT = "{} usize invalid"     # cartpole.rs:404

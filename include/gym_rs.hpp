@@ -18,6 +18,7 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <limits>
 #include <optional>
 #include <stdexcept>
@@ -106,6 +107,14 @@ template <class Derived, class Obs, int KIND, int DIM> class EnvBase {
     EnvBase &operator=(const EnvBase &) = delete;
     ~EnvBase() { close(); }
 
+    // where the log::warn! of the reference goes (default: stderr); set to nullptr to silence
+    using WarnSink = void (*)(const char *);
+    static WarnSink &warn_sink()
+    {
+        static WarnSink sink = [](const char *m) { std::fprintf(stderr, "WARN gym_rs: %s\n", m); };
+        return sink;
+    }
+
     // core.rs:42
     ActionReward<Obs, Unit> step(Action action)
     {
@@ -117,6 +126,10 @@ template <class Derived, class Obs, int KIND, int DIM> class EnvBase {
         check(gymrs_step_host(handle_, &a, 0, obs, &reward, &done, &truncated));
         check(gymrs_sync(handle_, nullptr));
         pull_state();
+        // reward 0 on a terminal step means the env had already terminated before this call: the
+        // reference logs a warning there (log::warn!, cartpole.rs:461)
+        if (Derived::WARNS_AFTER_TERMINATION && done && reward == 0.0f && warn_sink())
+            warn_sink()("Calling step after termination may result in undefined behaviour. Consider reseting.");
         return {Derived::make_obs(obs), (double)reward, done != 0, truncated != 0, Derived::step_info()};
     }
 
@@ -205,6 +218,7 @@ class CartPoleEnv : public core::EnvBase<CartPoleEnv, CartPoleObservation, GYMRS
         return sbt < 0 ? std::nullopt : std::optional<size_t>((size_t)sbt);
     }
     static CartPoleObservation make_obs(const float *v) { return {v[0], v[1], v[2], v[3]}; }
+    static constexpr bool WARNS_AFTER_TERMINATION = true; // :455-464
     static std::optional<core::Unit> step_info() { return core::Unit{}; } // info: Some(()), :481
     static std::string invalid_action_message(size_t a) { return std::to_string(a) + " usize invalid"; } // :404
 };
@@ -227,6 +241,7 @@ class MountainCarEnv : public core::EnvBase<MountainCarEnv, MountainCarObservati
     spaces::Discrete action_space{3}; // :363
     spaces::BoxR<MountainCarObservation> observation_space;
     static MountainCarObservation make_obs(const float *v) { return {v[0], v[1]}; }
+    static constexpr bool WARNS_AFTER_TERMINATION = false; // reward is -1 whatever happened before, mountain_car.rs:423
     static std::optional<core::Unit> step_info() { return std::nullopt; } // info: None, :433
     static std::string invalid_action_message(size_t a) { return std::to_string(a) + " (usize) invalid"; } // :404
 };

@@ -22,6 +22,7 @@ pub struct BatchStep<'a> {
 
 pub struct BatchedEnv {
     handle: *mut ffi::gymrs_env,
+    kind: Kind,
     num_envs: usize,
     global_env_offset: u64,
     obs_dim: usize,
@@ -48,6 +49,7 @@ impl BatchedEnv {
         let obs_dim = match kind { Kind::CartPole => 4, Kind::MountainCar => 2, Kind::Pendulum => 3 };
         Self {
             handle,
+            kind,
             num_envs,
             global_env_offset,
             obs_dim,
@@ -66,8 +68,10 @@ impl BatchedEnv {
         used
     }
 
-    /// Discrete envs.  Panics like the reference on an action outside the action space.
+    /// Discrete envs (`Action = usize`, cartpole.rs:390, mountain_car.rs:393).  Panics like the
+    /// reference on an action outside the action space.
     pub fn step(&mut self, actions: &[usize], autoreset: bool) -> BatchStep<'_> {
+        assert!(self.kind != Kind::Pendulum, "Pendulum takes f32 torques: use step_f32");
         assert_eq!(actions.len(), self.num_envs);
         for (d, a) in self.actions.iter_mut().zip(actions) {
             *d = i32::try_from(*a).unwrap_or(i32::MAX); // out-of-range values are rejected on the device
@@ -86,6 +90,51 @@ impl BatchedEnv {
             ffi::check(rc);
         }
         BatchStep { observation: &self.obs, reward: &self.reward, done: &self.done, truncated: &self.truncated }
+    }
+
+    /// Continuous envs (Pendulum): one f32 torque per env, clipped to the action box on the device.
+    pub fn step_f32(&mut self, actions: &[f32], autoreset: bool) -> BatchStep<'_> {
+        assert!(self.kind == Kind::Pendulum, "discrete envs take usize actions: use step");
+        assert_eq!(actions.len(), self.num_envs);
+        let flags = if autoreset { ffi::GYMRS_STEP_AUTORESET } else { 0 };
+        unsafe {
+            ffi::check(ffi::gymrs_step_host(self.handle, actions.as_ptr() as *const c_void, flags,
+                                            self.obs.as_mut_ptr(), self.reward.as_mut_ptr(),
+                                            self.done.as_mut_ptr(), self.truncated.as_mut_ptr()));
+            ffi::check(ffi::gymrs_sync(self.handle, std::ptr::null_mut()));
+        }
+        BatchStep { observation: &self.obs, reward: &self.reward, done: &self.done, truncated: &self.truncated }
+    }
+
+    /// Step with actions that already live on the device (`int32[num_envs]`, or `float[num_envs]` for
+    /// Pendulum): no host copies at all.  Asynchronous; results land in [`BatchedEnv::buffers`].
+    ///
+    /// # Safety
+    /// `actions_dev` must be a device pointer readable from the handle's GPU, valid until the step has
+    /// run ([`BatchedEnv::sync`]).
+    pub unsafe fn step_device(&mut self, actions_dev: *const c_void, autoreset: bool) {
+        let flags = if autoreset { ffi::GYMRS_STEP_AUTORESET } else { 0 };
+        ffi::check(ffi::gymrs_step(self.handle, actions_dev, flags));
+    }
+
+    /// Device pointers to the handle's SoA arrays (observation, reward, done, truncated, ...).
+    pub fn buffers(&self) -> ffi::gymrs_buffers {
+        let mut b = std::mem::MaybeUninit::<ffi::gymrs_buffers>::zeroed();
+        unsafe {
+            ffi::check(ffi::gymrs_get_buffers(self.handle, b.as_mut_ptr()));
+            b.assume_init()
+        }
+    }
+
+    /// Wait for queued device steps; panics like the reference if one of them met an invalid action.
+    pub fn sync(&mut self) {
+        let mut bad = 0u64;
+        let rc = unsafe { ffi::gymrs_sync(self.handle, &mut bad) };
+        if rc == ffi::GYMRS_ERR_INVALID_ACTION {
+            let msg = unsafe { std::ffi::CStr::from_ptr(ffi::gymrs_last_error()) };
+            panic!("{}", msg.to_string_lossy()); // "<action> usize invalid (env <global id>)"
+        }
+        ffi::check(rc);
     }
 
     /// The whole handle as one blob (`Env: Serialize`, core.rs:25).  Unlike the reference's serde
@@ -109,6 +158,9 @@ impl BatchedEnv {
     }
     pub fn obs_dim(&self) -> usize {
         self.obs_dim
+    }
+    pub fn kind(&self) -> Kind {
+        self.kind
     }
     /// Raw handle for callers that keep actions / results on the device (`gymrs_step`, `gymrs_rollout`).
     pub fn raw(&self) -> *mut ffi::gymrs_env {

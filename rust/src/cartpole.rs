@@ -16,8 +16,11 @@ use crate::ffi;
 
 const RENDER_MODES: &[RenderMode] = &[RenderMode::None];
 
-/// One CartPole instance living in GPU memory.  Field names follow the reference struct; the
-/// physics constants are pushed to the device by [`CartPoleEnv::sync_params`] after mutation.
+/// One CartPole instance living in GPU memory.  Field names follow the reference struct.  The
+/// reference's `pub` fields are plain data a caller may assign between steps (`env.gravity = ...`,
+/// `env.state = ...`, cartpole.rs:60-81) and the next `step` uses them; here `step` / `reset` compare
+/// the fields with the copy last exchanged with the device and push whatever changed, so assignments
+/// take effect exactly as in the reference ([`CartPoleEnv::sync_params`] remains for eager pushes).
 #[derive(Debug, Serialize)]
 pub struct CartPoleEnv {
     pub action_space: Discrete,
@@ -39,6 +42,13 @@ pub struct CartPoleEnv {
     rand_random: Pcg64,
     #[serde(skip_serializing)]
     handle: *mut ffi::gymrs_env,
+    /// what the device holds: the parameter block last pushed, the state / counter last pulled
+    #[serde(skip_serializing)]
+    device_params: ffi::gymrs_cartpole_params,
+    #[serde(skip_serializing)]
+    device_state: CartPoleObservation,
+    #[serde(skip_serializing)]
+    device_sbt: Option<usize>,
 }
 
 fn obs_from(v: &[f32; 4]) -> CartPoleObservation {
@@ -86,15 +96,17 @@ impl CartPoleEnv {
             steps_beyond_terminated: None,
             rand_random: rng,
             handle,
+            device_params: p,
+            device_state: obs_from(&[0.0; 4]),
+            device_sbt: None,
         };
         env.pull_state();
         env
     }
 
-    /// Push the (possibly mutated) `pub` physics fields to the device.
-    pub fn sync_params(&mut self) {
-        let mut p = ffi::gymrs_cartpole_params::default();
-        unsafe { ffi::check(ffi::gymrs_get_params(self.handle, &mut p as *mut _ as *mut c_void)) };
+    /// The parameter block the `pub` fields describe right now.
+    fn params_from_fields(&self) -> ffi::gymrs_cartpole_params {
+        let mut p = self.device_params; // keeps max_episode_steps
         p.gravity = self.gravity.into_inner();
         p.masscart = self.masscart.into_inner();
         p.masspole = self.masspole.into_inner();
@@ -107,7 +119,31 @@ impl CartPoleEnv {
         };
         p.theta_threshold_radians = self.theta_threshold_radians.into_inner();
         p.x_threshold = self.x_threshold.into_inner();
+        p
+    }
+
+    /// Push the `pub` physics fields to the device now (`step` and `reset` do it on their own when a
+    /// field changed).
+    pub fn sync_params(&mut self) {
+        let p = self.params_from_fields();
         unsafe { ffi::check(ffi::gymrs_set_params(self.handle, &p as *const _ as *const c_void)) };
+        self.device_params = p;
+    }
+
+    /// Bring the device in line with fields the caller assigned since the last exchange:
+    /// physics constants (cartpole.rs:63-80), `state` (:60) and `steps_beyond_terminated` (:81).
+    fn push_if_changed(&mut self) {
+        if self.params_from_fields() != self.device_params {
+            self.sync_params();
+        }
+        if self.state != self.device_state || self.steps_beyond_terminated != self.device_sbt {
+            let v: Vec<f64> = self.state.into();
+            let s = [v[0] as f32, v[1] as f32, v[2] as f32, v[3] as f32];
+            let sbt = [self.steps_beyond_terminated.map_or(-1i32, |k| k as i32)];
+            unsafe { ffi::check(ffi::gymrs_set_state(self.handle, s.as_ptr(), sbt.as_ptr())) };
+            self.device_state = self.state;
+            self.device_sbt = self.steps_beyond_terminated;
+        }
     }
 
     fn pull_state(&mut self) {
@@ -116,6 +152,8 @@ impl CartPoleEnv {
         unsafe { ffi::check(ffi::gymrs_get_state(self.handle, s.as_mut_ptr(), sbt.as_mut_ptr())) };
         self.state = obs_from(&s);
         self.steps_beyond_terminated = if sbt[0] < 0 { None } else { Some(sbt[0] as usize) };
+        self.device_state = self.state;
+        self.device_sbt = self.steps_beyond_terminated;
     }
 }
 
@@ -128,6 +166,8 @@ impl Env for CartPoleEnv {
     fn step(&mut self, action: Self::Action) -> ActionReward<Self::Observation, Self::Info> {
         // same check and message as the reference (cartpole.rs:402-406); the device validates again
         assert!(unsafe { ffi::gymrs_discrete_contains(2, action as u64) } != 0, "{} usize invalid", action);
+        self.push_if_changed();
+        let was_terminated = self.steps_beyond_terminated.is_some();
         let act = [action as i32];
         let (mut obs, mut reward, mut done, mut truncated) = ([0f32; 4], [0f32; 1], [0u8; 1], [0u8; 1]);
         unsafe {
@@ -136,6 +176,10 @@ impl Env for CartPoleEnv {
             ffi::check(ffi::gymrs_sync(self.handle, std::ptr::null_mut()));
         }
         self.pull_state();
+        if done[0] != 0 && was_terminated {
+            // the reference's message, word for word (cartpole.rs:461)
+            log::warn!("Calling step after termination may result in undefined behaviour. Consider reseting.");
+        }
         ActionReward {
             observation: obs_from(&obs),
             reward: OrderedFloat(reward[0] as f64),
@@ -149,6 +193,9 @@ impl Env for CartPoleEnv {
              -> (Self::Observation, Option<Self::ResetInfo>) {
         let (rng, seed_no) = rand_random(seed);
         self.rand_random = rng;
+        if self.params_from_fields() != self.device_params {
+            self.sync_params();
+        }
         let bounds = options.map(|b| {
             let lo: Vec<f64> = b.low.into();
             let hi: Vec<f64> = b.high.into();
@@ -197,6 +244,9 @@ impl Clone for CartPoleEnv {
             steps_beyond_terminated: self.steps_beyond_terminated,
             rand_random: self.rand_random.clone(),
             handle,
+            device_params: self.device_params,
+            device_state: self.device_state,
+            device_sbt: self.device_sbt,
         }
     }
 }

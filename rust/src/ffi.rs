@@ -43,7 +43,7 @@ pub struct gymrs_host_rollout_desc {
 }
 
 #[repr(C)]
-#[derive(Clone, Copy, Debug, Default)]
+#[derive(Clone, Copy, Debug, Default, PartialEq)]
 pub struct gymrs_cartpole_params {
     pub gravity: f64,
     pub masscart: f64,
@@ -58,7 +58,7 @@ pub struct gymrs_cartpole_params {
 }
 
 #[repr(C)]
-#[derive(Clone, Copy, Debug, Default)]
+#[derive(Clone, Copy, Debug, Default, PartialEq)]
 pub struct gymrs_mountain_car_params {
     pub min_position: f64,
     pub max_position: f64,

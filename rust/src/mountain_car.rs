@@ -16,6 +16,9 @@ use crate::ffi;
 
 const RENDER_MODES: &[RenderMode] = &[RenderMode::None];
 
+/// One MountainCar instance living in GPU memory.  As in the reference, the `pub` fields are plain
+/// data a caller may assign between steps (mountain_car.rs:49-74); `step` / `reset` push whatever
+/// changed since the last exchange with the device.
 #[derive(Debug, Serialize)]
 pub struct MountainCarEnv {
     pub min_position: O64,
@@ -34,6 +37,11 @@ pub struct MountainCarEnv {
     rand_random: Pcg64,
     #[serde(skip_serializing)]
     handle: *mut ffi::gymrs_env,
+    /// what the device holds: the parameter block last pushed, the state last pulled
+    #[serde(skip_serializing)]
+    device_params: ffi::gymrs_mountain_car_params,
+    #[serde(skip_serializing)]
+    device_state: MountainCarObservation,
 }
 
 fn obs_from(v: &[f32; 2]) -> MountainCarObservation {
@@ -68,15 +76,16 @@ impl MountainCarEnv {
             metadata: Metadata::new(RENDER_MODES, 30),
             rand_random: rng,
             handle,
+            device_params: p,
+            device_state: obs_from(&[0.0; 2]),
         };
         env.pull_state();
         env
     }
 
-    /// Push the (possibly mutated) `pub` physics fields to the device.
-    pub fn sync_params(&mut self) {
-        let mut p = ffi::gymrs_mountain_car_params::default();
-        unsafe { ffi::check(ffi::gymrs_get_params(self.handle, &mut p as *mut _ as *mut c_void)) };
+    /// The parameter block the `pub` fields describe right now.
+    fn params_from_fields(&self) -> ffi::gymrs_mountain_car_params {
+        let mut p = self.device_params; // keeps max_episode_steps
         p.min_position = self.min_position.into_inner();
         p.max_position = self.max_position.into_inner();
         p.max_speed = self.max_speed.into_inner();
@@ -84,13 +93,34 @@ impl MountainCarEnv {
         p.goal_velocity = self.goal_velocity.into_inner();
         p.force = self.force.into_inner();
         p.gravity = self.gravity.into_inner();
+        p
+    }
+
+    /// Push the `pub` physics fields to the device now (`step` and `reset` do it on their own when a
+    /// field changed).
+    pub fn sync_params(&mut self) {
+        let p = self.params_from_fields();
         unsafe { ffi::check(ffi::gymrs_set_params(self.handle, &p as *const _ as *const c_void)) };
+        self.device_params = p;
+    }
+
+    /// Bring the device in line with fields the caller assigned since the last exchange.
+    fn push_if_changed(&mut self) {
+        if self.params_from_fields() != self.device_params {
+            self.sync_params();
+        }
+        if self.state != self.device_state {
+            let s = [self.state.position.into_inner() as f32, self.state.velocity.into_inner() as f32];
+            unsafe { ffi::check(ffi::gymrs_set_state(self.handle, s.as_ptr(), std::ptr::null())) };
+            self.device_state = self.state;
+        }
     }
 
     fn pull_state(&mut self) {
         let mut s = [0f32; 2];
         unsafe { ffi::check(ffi::gymrs_get_state(self.handle, s.as_mut_ptr(), std::ptr::null_mut())) };
         self.state = obs_from(&s);
+        self.device_state = self.state;
     }
 }
 
@@ -103,6 +133,7 @@ impl Env for MountainCarEnv {
     fn step(&mut self, action: Self::Action) -> ActionReward<Self::Observation, Self::Info> {
         // mountain_car.rs:402-406
         assert!(unsafe { ffi::gymrs_discrete_contains(3, action as u64) } != 0, "{} (usize) invalid", action);
+        self.push_if_changed();
         let act = [action as i32];
         let (mut obs, mut reward, mut done, mut truncated) = ([0f32; 2], [0f32; 1], [0u8; 1], [0u8; 1]);
         unsafe {
@@ -111,6 +142,7 @@ impl Env for MountainCarEnv {
             ffi::check(ffi::gymrs_sync(self.handle, std::ptr::null_mut()));
         }
         self.state = obs_from(&obs);
+        self.device_state = self.state;
         ActionReward {
             observation: self.state,
             reward: OrderedFloat(reward[0] as f64),
@@ -124,6 +156,9 @@ impl Env for MountainCarEnv {
              -> (Self::Observation, Option<Self::ResetInfo>) {
         let (rng, seed_no) = rand_random(seed);
         self.rand_random = rng;
+        if self.params_from_fields() != self.device_params {
+            self.sync_params();
+        }
         let bounds = options.map(|b| {
             ([b.low.position.into_inner() as f32, b.low.velocity.into_inner() as f32],
              [b.high.position.into_inner() as f32, b.high.velocity.into_inner() as f32])
@@ -168,6 +203,8 @@ impl Clone for MountainCarEnv {
             metadata: self.metadata.clone(),
             rand_random: self.rand_random.clone(),
             handle,
+            device_params: self.device_params,
+            device_state: self.device_state,
         }
     }
 }

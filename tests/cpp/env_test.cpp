@@ -77,8 +77,18 @@ static void cartpole_plumbing()
     // stepping after termination: reward 1.0 on the first done step, 0.0 afterwards (cartpole.rs:455-464)
     env.reset(3, false, std::nullopt);
     double last = 1.0; bool seen_done = false;
-    for (int t = 0; t < 80; ++t) { auto sr = env.step(1); if (seen_done) last = sr.reward; seen_done |= sr.done; }
+    static int warnings = 0; // ... and the reference logs a warning for each of those steps (log::warn!, :461)
+    auto keep = CartPoleEnv::warn_sink();
+    CartPoleEnv::warn_sink() = [](const char *m) { if (std::string(m).find("after termination") != std::string::npos) ++warnings; };
+    int late_steps = 0;
+    for (int t = 0; t < 80; ++t) {
+        auto sr = env.step(1);
+        if (seen_done) { last = sr.reward; ++late_steps; }
+        seen_done |= sr.done;
+    }
+    CartPoleEnv::warn_sink() = keep;
     EXPECT(seen_done && last == 0.0);
+    EXPECT(late_steps > 0 && warnings == late_steps);
     // invalid action: the reference's assert! message (cartpole.rs:402-406)
     bool threw = false;
     try { env.step(2); } catch (const Panic &e) { threw = std::string(e.what()) == "2 usize invalid"; }

@@ -1178,3 +1178,40 @@ def test_scalar_env_surface_like_examples_cartpole(torch, g):
     with pytest.raises(AssertionError, match=r"3 \(usize\) invalid"):  # mountain_car.rs:402-406
         mc.step(3)
     mc.close()
+
+
+def test_stepping_after_termination_warns_like_the_reference(torch, g, caplog):
+    """cartpole.rs:455-464: the first terminal step still pays 1.0; every later step pays 0.0, bumps
+    steps_beyond_terminated and logs a warning (log::warn!, :461).  MountainCar has no such state."""
+    import logging
+    env = g.CartPoleEnv(g.RenderMode.NONE)
+    env.reset(seed=3)
+    with caplog.at_level(logging.WARNING, logger="gym_rs"):
+        for _ in range(400):
+            sr = env.step(1)
+            if sr.done:
+                break
+        assert sr.done and sr.reward == 1.0 and env.steps_beyond_terminated == 0
+        assert not caplog.records
+        sr = env.step(1)
+        assert sr.done and sr.reward == 0.0 and env.steps_beyond_terminated == 1
+        assert len(caplog.records) == 1 and "after termination" in caplog.records[0].getMessage()
+        env.reset(seed=4)
+        env.step(0)
+        assert len(caplog.records) == 1
+    env.close()
+
+
+def test_num_envs_one_reset_returns_the_observation_type(torch, g):
+    """core.rs:45-50: reset returns (Observation, Option<ResetInfo>) -- for Pendulum the observation is
+    (cos, sin, theta_dot), not the (theta, theta_dot) state."""
+    from gym_rs_b200.envs.classical_control.pendulum import PendulumObservation
+    env = g.PendulumEnv()
+    obs, info = env.reset(seed=5, return_info=True)
+    assert isinstance(obs, PendulumObservation) and info == ()
+    st = env.get_state()[:, 0]
+    assert abs(obs.to_vec()[0] - math.cos(st[0])) < 1e-6 and abs(obs.to_vec()[1] - math.sin(st[0])) < 1e-6
+    assert abs(obs.to_vec()[2] - st[1]) < 1e-7
+    sr = env.step(0.5)
+    assert isinstance(sr.observation, PendulumObservation)
+    env.close()
