@@ -352,16 +352,26 @@ def run_b200(args):
     # launch schedule: consecutive steps go to consecutive ring slots; visit v of a slot uses action set v
     handles = [(e.handle, acts[v].data_ptr()) for v in range(ACTION_SETS) for e, acts in ring]
     resident_pool = [(ring[0][0].handle, a.data_ptr()) for a in ring[0][1]]
-    step = L.gymrs_step
     AR = _capi.STEP_AUTORESET
+    import ctypes as C
+    step_many = L.gymrs_step_many
+    _arrays = {}
 
     def run_steps(k, pool):
+        """k consecutive steps over the pool's (handle, action batch) pairs in order: gymrs_step_many, i.e.
+        one gymrs_step per pair with one FFI crossing per pass over the pool (no Python between launches)."""
         m = len(pool)
-        for i in range(k):
-            h, a = pool[i % m]
-            rc = step(h, a, AR)
+        if id(pool) not in _arrays:
+            _arrays[id(pool)] = ((C.c_void_p * m)(*[h.value if hasattr(h, "value") else h for h, _ in pool]),
+                                 (C.c_void_p * m)(*[a for _, a in pool]))
+        hs, acts = _arrays[id(pool)]
+        left = k
+        while left > 0:
+            c = min(m, left)
+            rc = step_many(hs, acts, c, AR, None)
             if rc:
                 _capi.check(rc)
+            left -= c
 
     def barrier():
         if world > 1:
@@ -608,7 +618,8 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic",
             "config": config_of(args, world),
             "method": {
-                "launch": "one step kernel per step (gymrs_step); the independent ring slots alternate over "
+                "launch": "one step kernel per step (gymrs_step semantics, enqueued through gymrs_step_many: one FFI "
+                          "crossing per pass over the ring); the independent ring slots alternate over "
                           f"{len(streams)} CUDA stream(s) so consecutive launches overlap; pdl={args.pdl}",
                 "repeats": repeats, "timing": "CUDA events on the main stream (the other streams fork from the start "
                 "event and join before the end event), barrier + device synchronize on both sides of every region, "

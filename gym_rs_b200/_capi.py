@@ -78,6 +78,7 @@ SIGNATURES = {
     "gymrs_get_stream": (_i, [_vp, C.POINTER(_vp)]),
     "gymrs_reset": (_i, [_vp, _pu64, _vp, _vp, _vp, _pu64]),
     "gymrs_step": (_i, [_vp, _vp, _u32]),
+    "gymrs_step_many": (_i, [C.POINTER(_vp), C.POINTER(_vp), _u32, _u32, C.POINTER(_u32)]),
     "gymrs_step_host": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "gymrs_step_host_async": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _pu64]),
     "gymrs_host_wait": (_i, [_vp, _u64]),

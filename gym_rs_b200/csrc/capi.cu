@@ -824,6 +824,18 @@ int gymrs_step(gymrs_env *e, const void *actions, uint32_t step_flags)
 // here blocks the host, step t + 1 can be submitted while step t's results are still streaming
 // out: the D2H engine (the bottleneck at 21 B per env-step vs 4 B in) never idles.  Chunk
 // boundaries are multiples of 1024 envs so every chunk keeps the 128-bit access path.
+int gymrs_step_many(gymrs_env *const *envs, const void *const *actions, uint32_t count, uint32_t step_flags,
+                    uint32_t *done)
+{
+    if (done) *done = 0;
+    if (count && (!envs || !actions)) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    for (uint32_t i = 0; i < count; ++i) {
+        if (int rc = gymrs_step(envs[i], actions[i], step_flags)) return rc;
+        if (done) *done = i + 1;
+    }
+    return GYMRS_OK;
+}
+
 } // extern "C"
 
 namespace {

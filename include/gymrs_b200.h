@@ -149,6 +149,14 @@ int gymrs_reset(gymrs_env *env, const uint64_t *seed, const float *low, const fl
  * next gymrs_sync reports (the reference panics). */
 int gymrs_step(gymrs_env *env, const void *actions, uint32_t step_flags);
 
+/* One gymrs_step for each of `count` (handle, action batch) pairs, in order, with a single FFI crossing:
+ * for callers that keep a batch in several handles (one per GPU, or several env groups per GPU whose
+ * launches then overlap on the handles' streams).  A handle may appear more than once (consecutive
+ * steps of pre-generated actions).  Stops at the first error and returns it; *done (optional) receives
+ * the number of steps that were enqueued. */
+int gymrs_step_many(gymrs_env *const *envs, const void *const *actions, uint32_t count, uint32_t step_flags,
+                    uint32_t *done);
+
 /* Same step with HOST buffers: copies actions in, steps, copies observation / reward / done
  * out (any output pointer may be NULL to skip it) and synchronises.  obs: [obs_dim][num_envs]. */
 int gymrs_step_host(gymrs_env *env, const void *actions, uint32_t step_flags,

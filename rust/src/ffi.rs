@@ -128,6 +128,8 @@ extern "C" {
     pub fn gymrs_reset(env: *mut gymrs_env, seed: *const u64, low: *const f32, high: *const f32,
                        mask: *const u8, seed_used: *mut u64) -> c_int;
     pub fn gymrs_step(env: *mut gymrs_env, actions: *const c_void, step_flags: u32) -> c_int;
+    pub fn gymrs_step_many(envs: *const *mut gymrs_env, actions: *const *const c_void, count: u32, step_flags: u32,
+                           done: *mut u32) -> c_int;
     pub fn gymrs_step_host(env: *mut gymrs_env, actions: *const c_void, step_flags: u32, obs: *mut f32,
                            reward: *mut f32, done: *mut u8, truncated: *mut u8) -> c_int;
     pub fn gymrs_step_host_async(env: *mut gymrs_env, actions: *const c_void, step_flags: u32, obs: *mut f32,
