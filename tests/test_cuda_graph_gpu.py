@@ -168,3 +168,78 @@ def test_replay_after_reseeding_is_reported_not_silently_wrong(torch, g):
         graph.replay()
         env.sync()              # same seed again: fine
     env.close()
+
+
+def test_replay_after_a_parameter_or_variant_change_is_reported(torch, g):
+    """A captured step freezes what the host decided at capture: the folded parameter block and the kernel
+    variant (an auto-reset step of a handle whose steps_beyond_terminated is all-None skips that row).
+    Changing either afterwards bumps the handle's parameter generation; a stale replay raises a sticky
+    error instead of silently stepping with the old constants / the wrong variant."""
+    from gym_rs_b200 import _capi
+    n = 4096
+    acts = random_actions(torch, "cartpole", 2, n, 1)
+    side = torch.cuda.Stream()
+
+    def captured_step(env):
+        env.sync()
+        env.set_stream(side.cuda_stream)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            env.step(acts[0], autoreset=True)
+        return graph
+
+    # 1. gymrs_set_params after capture
+    env = make(g, "cartpole", n)
+    env.reset(seed=1)
+    graph = captured_step(env)
+    with torch.cuda.stream(side):
+        graph.replay()
+        env.sync()
+        p = env.params
+        p.gravity = 3.7
+        env.params = p
+        graph.replay()
+        with pytest.raises(_capi.GymrsError, match="re-capture"):
+            env.sync()
+        fresh = captured_step(env)          # recorded under the new constants: fine
+    with torch.cuda.stream(side):
+        fresh.replay()
+        env.sync()
+    env.close()
+
+    # 2. the first step WITHOUT auto-reset makes steps_beyond_terminated matter: the graph that recorded
+    #    the variant without that row is stale; one recorded afterwards clears the row and matches eager steps
+    env = make(g, "cartpole", n)
+    ref = make(g, "cartpole", n)
+    for e in (env, ref):
+        e.reset(seed=2)
+    graph = captured_step(env)
+    with torch.cuda.stream(side):
+        graph.replay()
+        ref_out = None
+    ref.step(acts[0], autoreset=True)
+    with torch.cuda.stream(side):
+        env.step(acts[1], autoreset=False)
+        graph.replay()
+        with pytest.raises(_capi.GymrsError, match="re-capture"):
+            env.sync()
+    env.close()
+    ref.close()
+    env = make(g, "cartpole", n)
+    ref = make(g, "cartpole", n)
+    for e in (env, ref):
+        e.reset(seed=2)
+        for _ in range(60):                 # without resets nearly every pole falls: sbt = Some(k) everywhere
+            e.step(acts[1], autoreset=False)
+    graph = captured_step(env)              # recorded with the steps_beyond_terminated row
+    for _ in range(3):
+        with torch.cuda.stream(side):
+            graph.replay()
+        ref.step(acts[0], autoreset=True)
+    env.sync()
+    ref.sync()
+    assert np.array_equal(env.get_state(), ref.get_state())
+    assert np.array_equal(env.steps_beyond_terminated.cpu().numpy(), ref.steps_beyond_terminated.cpu().numpy())
+    assert np.array_equal(env._t_reward.cpu().numpy(), ref._t_reward.cpu().numpy())
+    env.close()
+    ref.close()

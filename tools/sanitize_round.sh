@@ -1,5 +1,5 @@
 #!/bin/bash
-# compute-sanitizer passes behind profiles/r01_sanitizer_*.log
+# compute-sanitizer passes behind profiles/r0N_sanitizer_*.log
 mkdir -p gpurun_out
 for tool in memcheck racecheck initcheck synccheck; do
   timeout 600 compute-sanitizer --tool $tool python tools/sanitize_small.py > gpurun_out/sanitizer_$tool.log 2>&1

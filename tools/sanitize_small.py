@@ -12,7 +12,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gym_rs_b200 as g  # noqa: E402
 
-n = 8192 + 4
+n = 8192 + 6  # not a multiple of 4: the last thread takes the scalar out-of-line path
 gen = torch.Generator(device="cuda").manual_seed(0)
 for cls, hi in ((g.CartPoleEnv, 2), (g.MountainCarEnv, 3), (g.PendulumEnv, 0)):
     for vec, pdl in ((0, 1), (4, 2), (8, 2), (8, 0), (1, 2)):
@@ -35,6 +35,25 @@ for cls, hi in ((g.CartPoleEnv, 2), (g.MountainCarEnv, 3), (g.PendulumEnv, 0)):
         env.step_host(h[0], obs, rew, done, None, autoreset=True)
         env.sync()
         assert np.isfinite(env.get_state()).all()
+        # far-out states: whole threads leave the straight-line path (out-of-line scalar steps, libm trig)
+        st = env.get_state()
+        st[0, ::7] = 3000.0
+        st[-1, ::5] = -50.0
+        env.set_state(st)
+        env.step(acts[0], autoreset=False)
+        env.rollout(torch.stack(acts), autoreset=False)
+        # pipelined host loop with the compact wire formats (widen / pack kernels)
+        S = 2
+        hobs = torch.empty((S, env.obs_dim, n)).pin_memory()
+        hrew = torch.empty((S, n)).pin_memory()
+        if hi:
+            hbits = torch.empty((S, (n + 7) // 8), dtype=torch.uint8).pin_memory()
+            hact = torch.stack(h).to(torch.uint8).pin_memory()
+            env.rollout_host(hact, hobs, hrew, hbits, None, n_steps=5, u8_actions=True, packed_done=True)
+        else:
+            hdone = torch.empty((S, n), dtype=torch.uint8).pin_memory()
+            env.rollout_host(torch.stack(h).pin_memory(), hobs, hrew, hdone, None, n_steps=5)
+        env.sync()
         env.close()
 # device-counted kernel variants (CUDA-graph capture): captured steps + rollout + seeded reset,
 # replayed, then an eager step, a host step, a checkpoint round trip and a clone on the same handle
