@@ -281,6 +281,16 @@ def kernel_isolated_us(env):
         return None
 
 
+def mode_floor(env):
+    """What kernels that only move this env's bytes cost in each stepping mode (tools/mode_floor.cu, committed
+    measurement: profiles/mode_floor.json): the denominators for the one-stream and isolated figures."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "mode_floor.json")))
+        return dict(d[env], source=d["source"]) if env in d else None
+    except Exception:
+        return None
+
+
 def pcie_ceiling(torch, dist, device, world, h2d_bytes, d2h_bytes, iters=12):
     """What plain copies of one step's bytes reach on this box with ALL ranks copying at once:
     per iteration one H2D copy of h2d_bytes and one D2H copy of d2h_bytes from / to pinned memory
@@ -635,7 +645,7 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(env), "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": ALGO_BYTES[env], "kernel": "step_kernel",
-                         "kernel_us_isolated": kernel_isolated_us(env)},
+                         "kernel_us_isolated": kernel_isolated_us(env), "copy_only_floor_us": mode_floor(env)},
             "cpu_baseline": cpu,
             "rollout": rollout,
             "single_stream_default": {
