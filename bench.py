@@ -225,19 +225,20 @@ def run_reference(args):
     import oracle
     steps, warmup = args.steps, args.warmup
     kind = {"cartpole": oracle.CARTPOLE, "mountain_car": oracle.MOUNTAIN_CAR, "pendulum": oracle.PENDULUM}[args.env]
-    # first region: also calibrates (and, on a slow host, bounds the sample)
-    value, t, cores, sample, sample_envs = cpu_rollout(args.env, args.envs, steps, warmup, budget_s=20.0)
-    # A region of `steps` steps is short (20 steps of 1 M envs = ~30 ms on 32 cores): thread start-up
-    # and cold caches would dominate a single one, so the region is repeated like the B200 arm's
-    # and the median is reported.
-    # (each call also re-creates the env objects, untimed; the wall budget below counts that)
-    times, w0 = [t], time.perf_counter()
-    while len(times) < (args.ref_repeats or 200) and (args.ref_repeats or len(times) < 5
-                                                      or time.perf_counter() - w0 < 15.0):
-        ti, _ = oracle.bench_rollout(kind, sample_envs, steps, warmup, cores, 0)
-        times.append(ti)
+    # calibrate (and, on a slow host, bound the sample): one cold region from a fresh reset
+    _, t_cal, cores, sample, sample_envs = cpu_rollout(args.env, args.envs, steps, warmup, budget_s=20.0)
+    # A region of `steps` steps is short (20 steps of 1 M envs = ~40 ms on 16 cores) and, straight after the
+    # synchronised initial reset, it sees an episode-end burst instead of the stationary ~4.5 % resets
+    # per step.  So: ONE set of env objects and threads, an untimed burn-in that decorrelates the episode
+    # phases (the B200 arm's ring is burnt in the same way), then regions of { warmup untimed, steps timed }
+    # for ~15 s of wall time; the median region is reported.
+    per_step = t_cal / max(steps, 1)
+    burnin = int(min(300, max(50, 2.0 / max(per_step, 1e-6))))
+    regions = args.ref_repeats or int(min(200, max(5, 15.0 / max(per_step * (steps + warmup), 1e-6))))
+    times = oracle.bench_regions(kind, sample_envs, steps, warmup, burnin, regions, cores, 0)
     t = statistics.median(times)
     value = sample_envs * steps / t
+    sample += f"; {burnin} untimed burn-in steps, then the median of {len(times)} regions of {steps} steps (first region from a fresh reset, cold: {sample_envs * steps / t_cal / 1e9:.3f} G)"
     line = {
         "impl": "reference",
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
@@ -250,7 +251,7 @@ def run_reference(args):
                            "crate itself cannot be built in this image (no cargo, SDL2 dependency)",
                    "repeats": len(times), "region_s_min_median_max": [min(times), t, max(times)]},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": sample + f"; median of {len(times)} regions"},
+                         "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -123,6 +123,9 @@ def lib() -> C.CDLL:
     L.orc_bench_rollout.restype = C.c_double
     L.orc_bench_rollout.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                     C.c_uint64, dp]
+    L.orc_bench_regions.restype = C.c_double
+    L.orc_bench_regions.argtypes = [C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_uint64, dp, dp]
     _lib = L
     return L
 
@@ -191,6 +194,18 @@ def philox4x32_10(ctr, key):
     k = (C.c_uint32 * 2)(*[int(x) & 0xFFFFFFFF for x in key])
     L.orc_philox4x32_10(c, k)
     return [int(x) for x in c]
+
+
+def bench_regions(kind, n_envs, n_steps, n_warmup, n_burnin, n_regions, n_threads, seed=0):
+    """The scalar reference loop over one set of env objects: n_burnin untimed steps, then n_regions
+    regions of n_warmup untimed + n_steps timed steps.  Returns the list of region seconds."""
+    L = lib()
+    cs = C.c_double(0.0)
+    out = (C.c_double * n_regions)()
+    t = L.orc_bench_regions(kind, n_envs, n_steps, n_warmup, n_burnin, n_regions, n_threads, seed, out, C.byref(cs))
+    if t < 0:
+        raise MemoryError("orc_bench_regions: allocation failed")
+    return [float(x) for x in out]
 
 
 def bench_rollout(kind, n_envs, n_steps, n_warmup, n_threads, seed=0):

@@ -562,6 +562,8 @@ typedef struct {
     pthread_barrier_t *bar;
     double checksum;
     double t0, t1;
+    int n_burnin, n_regions;
+    double *region_s;
 } bench_arg;
 
 static inline uint64_t xorshift64(uint64_t *s)
@@ -580,62 +582,86 @@ static double now_s(void)
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
+/* one batch step of this thread's shard: every env object steps once with a random action and is
+ * reset when it ends (examples/cartpole.rs:18-28) */
+static void bench_step_shard(bench_arg *a, uint64_t *rng, uint64_t epoch)
+{
+    double r = 0.;
+    int d = 0, t = 0;
+    if (a->kind == 0) {
+        orc_cartpole_env *envs = (orc_cartpole_env *)a->envs;
+        for (size_t i = a->begin; i < a->end; ++i) {
+            size_t act = (size_t)(xorshift64(rng) >> 63);
+            orc_cartpole_step(&envs[i], act, &r, &d, &t);
+            memcpy(&a->obs[4 * i], envs[i].state, 4 * sizeof(double));
+            a->reward[i] = r;
+            a->done[i] = (uint8_t)d;
+            if (d) orc_cartpole_reset(&envs[i], a->seed, i, epoch, NULL, NULL);
+        }
+    } else if (a->kind == 1) {
+        orc_mountain_car_env *envs = (orc_mountain_car_env *)a->envs;
+        for (size_t i = a->begin; i < a->end; ++i) {
+            size_t act = (size_t)((xorshift64(rng) >> 33) % 3u);
+            orc_mountain_car_step(&envs[i], act, &r, &d, &t);
+            memcpy(&a->obs[2 * i], envs[i].state, 2 * sizeof(double));
+            a->reward[i] = r;
+            a->done[i] = (uint8_t)d;
+            if (d) orc_mountain_car_reset(&envs[i], a->seed, i, epoch, NULL, NULL);
+        }
+    } else {
+        orc_pendulum_env *envs = (orc_pendulum_env *)a->envs;
+        for (size_t i = a->begin; i < a->end; ++i) {
+            double act = ((double)(xorshift64(rng) >> 11) * (1.0 / 9007199254740992.0)) * 4. - 2.;
+            orc_pendulum_step(&envs[i], act, &a->obs[3 * i], &r, &d, &t);
+            a->reward[i] = r;
+            a->done[i] = (uint8_t)d;
+        }
+    }
+}
+
+/* Regions: n_burnin untimed steps once (episode phases decorrelate, like the burn-in of the GPU arm's
+ * ring), then n_regions times { n_warmup untimed steps, n_steps timed steps }.  region_s[r] is the
+ * wall time of region r from the barrier in front of its first timed step to the barrier behind
+ * its last one (taken by the first shard's thread; every thread passes both barriers). */
 static void *bench_worker(void *vp)
 {
     bench_arg *a = (bench_arg *)vp;
     uint64_t rng = a->seed * 0x9E3779B97F4A7C15ull + 0x1234567ull * (a->begin + 1);
     if (rng == 0) rng = 1;
-    double r = 0.;
-    int d = 0, t = 0;
-    double cs = 0.;
-    for (int s = 0; s < a->n_warmup + a->n_steps; ++s) {
-        if (s == a->n_warmup) {
-            pthread_barrier_wait(a->bar);
-            a->t0 = now_s();
-        }
-        uint64_t epoch = (uint64_t)s + 1;
-        if (a->kind == 0) {
-            orc_cartpole_env *envs = (orc_cartpole_env *)a->envs;
-            for (size_t i = a->begin; i < a->end; ++i) {
-                size_t act = (size_t)(xorshift64(&rng) >> 63);
-                orc_cartpole_step(&envs[i], act, &r, &d, &t);
-                memcpy(&a->obs[4 * i], envs[i].state, 4 * sizeof(double));
-                a->reward[i] = r;
-                a->done[i] = (uint8_t)d;
-                if (d) orc_cartpole_reset(&envs[i], a->seed, i, epoch, NULL, NULL);
-            }
-        } else if (a->kind == 1) {
-            orc_mountain_car_env *envs = (orc_mountain_car_env *)a->envs;
-            for (size_t i = a->begin; i < a->end; ++i) {
-                size_t act = (size_t)((xorshift64(&rng) >> 33) % 3u);
-                orc_mountain_car_step(&envs[i], act, &r, &d, &t);
-                memcpy(&a->obs[2 * i], envs[i].state, 2 * sizeof(double));
-                a->reward[i] = r;
-                a->done[i] = (uint8_t)d;
-                if (d) orc_mountain_car_reset(&envs[i], a->seed, i, epoch, NULL, NULL);
-            }
-        } else {
-            orc_pendulum_env *envs = (orc_pendulum_env *)a->envs;
-            for (size_t i = a->begin; i < a->end; ++i) {
-                double act = ((double)(xorshift64(&rng) >> 11) * (1.0 / 9007199254740992.0)) * 4. - 2.;
-                orc_pendulum_step(&envs[i], act, &a->obs[3 * i], &r, &d, &t);
-                a->reward[i] = r;
-                a->done[i] = (uint8_t)d;
-            }
-        }
-        /* a batch step is complete only when every shard is: same barrier a
-         * host loop over many reference env objects would need */
+    uint64_t epoch = 0;
+    for (int s = 0; s < a->n_burnin; ++s) {
+        bench_step_shard(a, &rng, ++epoch);
         pthread_barrier_wait(a->bar);
     }
-    a->t1 = now_s();
+    for (int r = 0; r < a->n_regions; ++r) {
+        for (int s = 0; s < a->n_warmup; ++s) {
+            bench_step_shard(a, &rng, ++epoch);
+            pthread_barrier_wait(a->bar);
+        }
+        pthread_barrier_wait(a->bar);
+        const double t0 = now_s();
+        for (int s = 0; s < a->n_steps; ++s) {
+            bench_step_shard(a, &rng, ++epoch);
+            /* a batch step is complete only when every shard is: same barrier a
+             * host loop over many reference env objects would need */
+            pthread_barrier_wait(a->bar);
+        }
+        const double t1 = now_s();
+        if (r == 0) a->t0 = t0;
+        a->t1 = t1;
+        if (a->region_s && a->begin == 0) a->region_s[r] = t1 - t0;
+    }
+    double cs = 0.;
     for (size_t i = a->begin; i < a->end; ++i) cs += a->reward[i] + a->done[i];
     a->checksum = cs;
     return NULL;
 }
 
-double orc_bench_rollout(int kind, size_t n_envs, int n_steps, int n_warmup,
-                         int n_threads, uint64_t seed, double *checksum)
+double orc_bench_regions(int kind, size_t n_envs, int n_steps, int n_warmup, int n_burnin, int n_regions,
+                         int n_threads, uint64_t seed, double *region_s, double *checksum)
 {
+    if (n_regions < 1) n_regions = 1;
+    if (n_burnin < 0) n_burnin = 0;
     if (n_threads < 1) n_threads = 1;
     if ((size_t)n_threads > n_envs) n_threads = (int)n_envs;
     int obs_dim = kind == 0 ? 4 : (kind == 1 ? 2 : 3);
@@ -678,6 +704,9 @@ double orc_bench_rollout(int kind, size_t n_envs, int n_steps, int n_warmup,
         a->end = per * (t + 1) < n_envs ? per * (t + 1) : n_envs;
         a->n_steps = n_steps;
         a->n_warmup = n_warmup;
+        a->n_burnin = n_burnin;
+        a->n_regions = n_regions;
+        a->region_s = region_s;
         a->seed = seed;
         a->envs = envs;
         a->obs = obs;
@@ -698,4 +727,11 @@ double orc_bench_rollout(int kind, size_t n_envs, int n_steps, int n_warmup,
     pthread_barrier_destroy(&bar);
     free(th); free(args); free(envs); free(obs); free(reward); free(done);
     return t1 - t0;
+}
+
+/* one region, no burn-in: n_warmup untimed + n_steps timed steps from a fresh reset */
+double orc_bench_rollout(int kind, size_t n_envs, int n_steps, int n_warmup,
+                         int n_threads, uint64_t seed, double *checksum)
+{
+    return orc_bench_regions(kind, n_envs, n_steps, n_warmup, 0, 1, n_threads, seed, NULL, checksum);
 }

@@ -167,6 +167,14 @@ void orc_reset_batch(int kind, size_t n, double *state, uint64_t seed,
 double orc_bench_rollout(int kind, size_t n_envs, int n_steps, int n_warmup,
                          int n_threads, uint64_t seed, double *checksum);
 
+/* The same loop over ONE set of env objects and one set of threads, timed as regions:
+ * n_burnin untimed steps first (the synchronised initial reset makes most envs end around the
+ * same step; the burn-in lets episode phases decorrelate, like the GPU arm's), then n_regions
+ * times { n_warmup untimed steps, n_steps timed steps }.  region_s[n_regions] receives the wall
+ * seconds of each region's timed steps.  Returns first-timed-step to last-timed-step seconds. */
+double orc_bench_regions(int kind, size_t n_envs, int n_steps, int n_warmup, int n_burnin, int n_regions,
+                         int n_threads, uint64_t seed, double *region_s, double *checksum);
+
 #ifdef __cplusplus
 }
 #endif

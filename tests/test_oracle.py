@@ -259,6 +259,14 @@ def test_bench_rollout_runs():
     assert t > 0 and math.isfinite(cs)
 
 
+def test_bench_regions_times_every_region_over_one_set_of_envs():
+    # the reference arm of bench.py: burn-in, then regions of { warmup, timed steps }
+    for kind, threads in ((oracle.CARTPOLE, 2), (oracle.MOUNTAIN_CAR, 3), (oracle.PENDULUM, 1)):
+        times = oracle.bench_regions(kind, 4096, 5, 2, 7, 4, threads, seed=0)
+        assert len(times) == 4 and all(0.0 < t < 5.0 for t in times), times
+
+
+
 # ---- OrderedFloat total-order semantics (O64 = OrderedFloat<f64>, types.rs:4) ------------
 
 def test_nan_follows_ordered_float_total_order():
