@@ -450,12 +450,16 @@ def run_b200(args):
     clocks = cs.summary()
     ms = statistics.median(times)
 
-    def one_stream(pdl, pool, reps=3):
+    def one_stream(pdl, pool, reps=3, wide=False):
         for e, _ in ring:
             e.set_stream(stream.cuda_stream)
             e.set_launch_config(vec=args.vec, block=args.block, pdl=pdl)
+            e.set_launch_occupancy(wide)
         run_steps(len(pool), pool)
-        return statistics.median(over_ranks([timed(K, pool) for _ in range(reps)]))
+        t = statistics.median(over_ranks([timed(K, pool) for _ in range(reps)]))
+        for e, _ in ring:
+            e.set_launch_occupancy(False)
+        return t
 
     # Figures on ONE stream (what a caller with a single env group sees):
     #   default  -- pdl = 1, the library default: every launch waits for the whole previous grid.  Valid
@@ -469,6 +473,10 @@ def run_b200(args):
     default_res = one_stream(1, resident_pool)
     chained = one_stream(2, handles)
     resident = one_stream(2, resident_pool)
+    # the opt-in high-occupancy build (gymrs_set_launch_occupancy): meant for exactly this case, several
+    # independent batches stepped round-robin on ONE stream
+    wide_default_cold = one_stream(1, handles, wide=True)
+    wide_chained = one_stream(2, handles, wide=True)
     streams = saved_streams
     for e, _ in ring:
         e.sync()  # surfaces any invalid-action / CUDA error from the timed launches
@@ -656,6 +664,10 @@ def run_b200(args):
                                       "the 126 MB L2, so this is not an HBM number")},
             "single_stream_chained": figure(chained, "same cold ring on ONE stream with pipelined launches (pdl=2, per-CTA "
                                             "release/acquire flags instead of a grid-wide dependency; needs pre-generated actions)"),
+            "single_stream_wide": {
+                "default_cold_ring": figure(wide_default_cold, "cold ring on ONE stream, pdl=1, gymrs_set_launch_occupancy(1): the step "
+                                            "kernel under a 32 / 40-register budget (more resident CTAs; same bits)"),
+                "chained_cold_ring": figure(wide_chained, "cold ring on ONE stream, pdl=2, gymrs_set_launch_occupancy(1)")},
             "l2_resident": figure(resident, "ONE 1M-env batch stepped back to back on one stream, pdl=2 (a true "
                                   "dependency chain; the state stays in the 126 MB L2); not an HBM number"),
             "all_ms_per_step": [t / K for t in times][:40],

@@ -99,6 +99,7 @@ SIGNATURES = {
     "gymrs_kind_of": (_i, [_vp, C.POINTER(_i)]),
     "gymrs_sync": (_i, [_vp, _pu64]),
     "gymrs_set_launch_config": (_i, [_vp, _i, _i, _i]),
+    "gymrs_set_launch_occupancy": (_i, [_vp, _i]),
     "gymrs_host_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "gymrs_host_free": (_i, [_vp]),
     "gymrs_clip": (C.c_double, [C.c_double, C.c_double, C.c_double]),

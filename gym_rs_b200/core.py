@@ -194,6 +194,10 @@ class Env(EnvProperties):
     def set_launch_config(self, vec: int = 0, block: int = 0, pdl: int = 1):
         _capi.check(self._L.gymrs_set_launch_config(self._h, vec, block, pdl))
 
+    def set_launch_occupancy(self, wide: bool = False):
+        """Step kernel built for a tighter register budget (more resident CTAs); see gymrs_b200.h."""
+        _capi.check(self._L.gymrs_set_launch_occupancy(self._h, 1 if wide else 0))
+
     def sync(self):
         """Wait for queued work; raises like the reference's assert! if an action was invalid."""
         bad = C.c_uint64()

@@ -156,6 +156,7 @@ struct gymrs_env {
     cudaEvent_t switch_ev = nullptr; // orders a new stream after the old one (gymrs_set_stream)
     bool sbt_dirty = false;  // some env may hold steps_beyond_terminated = Some(_)
     int vec = 0, block = 0, pdl = 1;
+    bool wide = false;              // gymrs_set_launch_occupancy
 };
 
 namespace {
@@ -274,6 +275,7 @@ LaunchOpts make_opts(const gymrs_env *e, uint32_t step_flags)
     o.use_sbt = e->kind == GYMRS_CARTPOLE && (!o.autoreset || e->sbt_dirty);
     o.pdl = e->pdl;
     o.vec = e->vec;
+    o.wide = e->wide;
     // CTA size of a step launch.  128 threads (10 CTAs per SM instead of 5, twice as many progress
     // flags) measured 1 % faster than 256 on the two-stream ring and 3-8 % faster for chained and
     // L2-resident launches for CartPole and MountainCar; Pendulum is 1 % faster at 256
@@ -636,7 +638,7 @@ int gymrs_clone(const gymrs_env *src, gymrs_env **out)
     std::memcpy(e->reset_low, src->reset_low, sizeof e->reset_low);
     std::memcpy(e->reset_high, src->reset_high, sizeof e->reset_high);
     e->seed = src->seed; e->step_count = src->step_count; e->sbt_dirty = src->sbt_dirty;
-    e->vec = src->vec; e->block = src->block; e->pdl = src->pdl;
+    e->vec = src->vec; e->block = src->block; e->pdl = src->pdl; e->wide = src->wide;
     e->device_counted = src->device_counted;
     e->generation = src->generation;
     int rc = alloc_env(e);
@@ -737,6 +739,14 @@ int gymrs_set_launch_config(gymrs_env *e, int vec, int block, int pdl)
     if (block != 0 && (block < 32 || block > 256 || block % 32)) return fail(GYMRS_ERR_BAD_ARG, "block must be a multiple of 32 in [32, 256]");
     if (pdl < 0 || pdl > 2) return fail(GYMRS_ERR_BAD_ARG, "pdl must be 0, 1 or 2");
     e->vec = vec; e->block = block; e->pdl = pdl;
+    return GYMRS_OK;
+}
+
+int gymrs_set_launch_occupancy(gymrs_env *e, int wide)
+{
+    if (!e) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
+    if (wide != 0 && wide != 1) return fail(GYMRS_ERR_BAD_ARG, "wide must be 0 or 1");
+    e->wide = wide != 0;
     return GYMRS_OK;
 }
 

@@ -4,6 +4,10 @@
 //   SD / OD          rows of state / observation
 //   OBS_IS_STATE     the observation IS the post-step state (CartPole, MountainCar)
 //   HAS_SBT          keeps the reference's steps_beyond_terminated (CartPole)
+//   WIDE_MIN_CTAS    register budget of the opt-in high-occupancy step kernel, as the minimum number of
+//                    256-thread CTAs per SM in __launch_bounds__: 8 = 32 registers per thread (every CTA
+//                    of a 1M-env launch is resident at once), 6 = 40 registers; the tightest budget
+//                    ptxas meets without spilling on the default (auto-reset) path
 //   Action, P        action element type, by-value parameter block
 //   valid()          Space::contains on the action      (spaces/discrete.rs:14-20)
 //   pre()            the per-env action term the dynamics consume (force, push, clamped torque)
@@ -67,6 +71,7 @@ struct CartPole {
     static constexpr int SD = 4, OD = 4;
     static constexpr bool OBS_IS_STATE = true;
     static constexpr bool HAS_SBT = true;
+    static constexpr int WIDE_MIN_CTAS = 6;
     using Action = int32_t;
     using P = CartPoleP;
 
@@ -182,6 +187,7 @@ struct MountainCar {
     static constexpr int SD = 2, OD = 2;
     static constexpr bool OBS_IS_STATE = true;
     static constexpr bool HAS_SBT = false;
+    static constexpr int WIDE_MIN_CTAS = 8;
     using Action = int32_t;
     using P = MountainCarP;
 
@@ -272,6 +278,7 @@ struct Pendulum {
     static constexpr int SD = 2, OD = 3;
     static constexpr bool OBS_IS_STATE = false;
     static constexpr bool HAS_SBT = false;
+    static constexpr int WIDE_MIN_CTAS = 8;
     using Action = float;
     using P = PendulumP;
 

@@ -67,6 +67,7 @@ struct LaunchOpts {
     int pdl;          // 0 off; 1 programmatic dependent launch; 2 = 1 + actions read before the dependency wait
     int vec;          // envs per thread: 1, 2 or 4 (0 = pick); 8 = persistent TMA-staged kernel
     int block;        // threads per CTA (0 = default)
+    bool wide;        // step: the high-occupancy build (E::WIDE_MIN_CTAS), gymrs_set_launch_occupancy
 };
 
 // ---- launch geometry (shared by the launchers and the host library, which needs to know

@@ -482,8 +482,11 @@ __device__ __forceinline__ void step_body(const typename E::P &p, const BatchArg
     }
 }
 
-template <class E, int V, bool AR, bool SBT, bool TL, bool DEVC>
-__global__ void __launch_bounds__(256, GYMRS_STEP_MIN_CTAS)
+// MINB: minimum number of 256-thread CTAs per SM, i.e. the register budget (5 -> 48 registers, the
+// default; E::WIDE_MIN_CTAS -> 40 / 32, the opt-in high-occupancy build, LaunchOpts::wide).  Same
+// source, same arithmetic, same bits; only the occupancy differs (profiles/r02_sweeps.md).
+template <class E, int V, bool AR, bool SBT, bool TL, bool DEVC, int MINB = GYMRS_STEP_MIN_CTAS>
+__global__ void __launch_bounds__(256, MINB)
 step_kernel(const __grid_constant__ typename E::P p, const __grid_constant__ BatchArgs a)
 {
     using A = typename E::Action;
@@ -881,9 +884,10 @@ cudaError_t launch_ex(K kernel, uint64_t threads, int block, bool pdl, cudaStrea
     return cudaLaunchKernelEx(&cfg, kernel, p, a);
 }
 
-template <class E, int V, bool ROLLOUT, bool DEVC>
+template <class E, int V, bool ROLLOUT, bool DEVC, bool WIDE = false>
 cudaError_t dispatch_flags(const typename E::P &p, const BatchArgs &a_in, const LaunchOpts &o, cudaStream_t s)
 {
+    constexpr int MINB = WIDE ? E::WIDE_MIN_CTAS : GYMRS_STEP_MIN_CTAS;
     const uint64_t threads = (a_in.n + V - 1) / V;
     const int block = pick_block(o);
     const bool sbt = E::HAS_SBT && o.use_sbt;
@@ -894,7 +898,7 @@ cudaError_t dispatch_flags(const typename E::P &p, const BatchArgs &a_in, const 
 #define GYMRS_CASE(K, AR, SB, TL)                                                                   \
     case K:                                                                                         \
         return ROLLOUT ? launch_ex(rollout_kernel<E, V, AR, SB, TL, DEVC>, threads, block, false, s, p, a) \
-                       : launch_ex(step_kernel<E, V, AR, SB, TL, DEVC>, threads, block, o.pdl != 0, s, p, a);
+                       : launch_ex(step_kernel<E, V, AR, SB, TL, DEVC, MINB>, threads, block, o.pdl != 0, s, p, a);
     switch (key) {
         GYMRS_CASE(0, false, false, false)
         GYMRS_CASE(1, false, false, true)
@@ -980,6 +984,8 @@ cudaError_t dispatch_vec(const typename E::P &p, const BatchArgs &a, const Launc
         if (v == 4) return dispatch_flags<E, 4, ROLLOUT, true>(p, a, o, s);
         return dispatch_flags<E, 1, ROLLOUT, true>(p, a, o, s);
     }
+    // the high-occupancy build exists for the 128-bit host-counted step only
+    if (!ROLLOUT && v == 4 && o.wide) return dispatch_flags<E, 4, false, false, true>(p, a, o, s);
     switch (v) {
     case 4: return dispatch_flags<E, 4, ROLLOUT, false>(p, a, o, s);
     case 2: return dispatch_flags<E, 2, ROLLOUT, false>(p, a, o, s);

@@ -277,6 +277,20 @@ int gymrs_sync(gymrs_env *env, uint64_t *bad_env);
  *        non-kernel operation on the stream, still acts as a full barrier. */
 int gymrs_set_launch_config(gymrs_env *env, int vec, int block, int pdl);
 
+/* Occupancy of the step kernel (launch tuning, not part of the reference surface).
+ * wide = 0 (default): 48 registers per thread; a 1M-env launch is 1.38 waves of CTAs.  Fastest when
+ *   launches overlap anyway: several handles on several streams, or a chained (pdl = 2) loop over
+ *   ONE handle, where consecutive steps then pipeline CTA by CTA.
+ * wide = 1: the same kernel compiled to a tighter register budget (MountainCar / Pendulum 32
+ *   registers: every CTA of a 1M-env launch is resident at once; CartPole 40).  Faster where the
+ *   launches of one stream are independent of their immediate predecessor (several handles stepped
+ *   round-robin on one stream, pdl = 1 or 2: MountainCar -10 % / -16 % per step), slower for a
+ *   chained loop over one handle (the CTAs of a step then run in lockstep behind their
+ *   predecessors) and 2-5 % slower on two streams; same results bit for bit.  Applies to the
+ *   128-bit host-counted step; other launches (scalar widths, CUDA-graph-captured steps, rollouts,
+ *   the persistent kernel) ignore it. */
+int gymrs_set_launch_occupancy(gymrs_env *env, int wide);
+
 /* Pinned host memory for the *_host entry points. */
 int gymrs_host_alloc(size_t bytes, void **out);
 int gymrs_host_free(void *p);

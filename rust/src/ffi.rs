@@ -154,6 +154,7 @@ extern "C" {
     pub fn gymrs_kind_of(env: *const gymrs_env, kind: *mut c_int) -> c_int;
     pub fn gymrs_sync(env: *mut gymrs_env, bad_env: *mut u64) -> c_int;
     pub fn gymrs_set_launch_config(env: *mut gymrs_env, vec: c_int, block: c_int, pdl: c_int) -> c_int;
+    pub fn gymrs_set_launch_occupancy(env: *mut gymrs_env, wide: c_int) -> c_int;
     pub fn gymrs_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
     pub fn gymrs_host_free(p: *mut c_void) -> c_int;
     pub fn gymrs_clip(value: f64, left_bound: f64, right_bound: f64) -> f64;

@@ -524,6 +524,46 @@ def test_vec_widths_and_ragged_sizes_are_bit_identical(torch, g, kind):
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("kind", ["cartpole", "mountain_car", "pendulum"])
+@pytest.mark.parametrize("time_limit", [False, True])
+def test_wide_occupancy_build_is_bit_identical(torch, g, kind, time_limit):
+    """gymrs_set_launch_occupancy(1): the same step kernel under a tighter register budget (more resident
+    CTAs).  Same bits as the default build: plain and chained launches, auto-reset, with and without
+    the time limit, a ragged batch size, and a chain that switches between the two builds."""
+    n = (1 << 18) + 1001
+    cls = {"cartpole": g.CartPoleEnv, "mountain_car": g.MountainCarEnv, "pendulum": g.PendulumEnv}[kind]
+    r = np.random.default_rng(11)
+    if kind == "pendulum":
+        acts = [dev_actions(torch, r.uniform(-2, 2, n).astype(np.float32)) for _ in range(12)]
+    else:
+        acts = [dev_actions(torch, r.integers(0, 2 if kind == "cartpole" else 3, n).astype(np.int32))
+                for _ in range(12)]
+    results = []
+    for wide, pdl in ((False, 1), (True, 1), (True, 2), ("alternate", 2)):
+        env = cls(num_envs=n, time_limit=time_limit)
+        env.set_launch_config(vec=0, block=0, pdl=pdl)
+        env.reset(seed=3)
+        for k, a in enumerate(acts):
+            env.set_launch_occupancy(bool(k & 1) if wide == "alternate" else wide)
+            out = env.step(a, autoreset=(k % 5 != 4))  # every fifth step leaves finished envs alone
+        env.sync()
+        results.append((env.get_state(), out.observation.cpu().numpy(), out.reward.cpu().numpy(),
+                        out.done.cpu().numpy(), out.truncated.cpu().numpy()))
+        env.close()
+    assert results[0][3].any() or kind != "cartpole"
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert np.array_equal(a, b)
+    with pytest.raises(Exception):
+        e = cls(num_envs=8)
+        try:
+            e._L.gymrs_set_launch_occupancy.restype  # noqa: B018 (the symbol exists)
+            from gym_rs_b200 import _capi
+            _capi.check(e._L.gymrs_set_launch_occupancy(e._h, 2))
+        finally:
+            e.close()
+
+
 @pytest.mark.parametrize("kind,n,vec,block", [("cartpole", N_FULL, 0, 0), ("cartpole", 300001, 1, 32),
                                               ("mountain_car", 1 << 19, 2, 64), ("pendulum", 777777, 4, 128),
                                               # vec = 8: the persistent TMA-staged kernel (ragged last tile included)

@@ -10,6 +10,9 @@ for f in sys.argv[1:]:
         print(f, "unreadable:", exc)
         continue
     us = lambda x: x["ms_per_step"] * 1e3  # noqa: E731
+    if d.get("impl") == "reference":
+        print(f"{f}: reference arm {d['value'] / 1e9:.3f} G on {d['cpu_baseline']['cores']} cores  ({d['cpu_baseline']['sample']})")
+        continue
     print(f"{f}: n_gpus={d['n_gpus']} value {d['value'] / 1e9:.1f} G  {us(d):.3f} us/step  frac {d['roofline']['frac']:.3f}  "
           f"clocks {d['clocks']['sm_mhz']} {d['clocks']['reasons']}")
     ssd = d.get("single_stream_default")
@@ -17,6 +20,10 @@ for f in sys.argv[1:]:
         print(f"   one stream pdl=1: cold {us(ssd['cold_ring']):.3f} us ({ssd['cold_ring']['frac']:.3f})  resident {us(ssd['l2_resident']):.3f} us")
     print(f"   one stream pdl=2: cold {us(d['single_stream_chained']):.3f} us ({d['single_stream_chained']['frac']:.3f})  "
           f"resident {us(d['l2_resident']):.3f} us")
+    w = d.get("single_stream_wide")
+    if w:
+        print(f"   one stream, wide build: pdl=1 cold {us(w['default_cold_ring']):.3f} us ({w['default_cold_ring']['frac']:.3f})  "
+              f"pdl=2 cold {us(w['chained_cold_ring']):.3f} us ({w['chained_cold_ring']['frac']:.3f})")
     r = d.get("rollout")
     if r:
         print(f"   rollout {r['value'] / 1e9:.1f} G  write {r['write_gbs']:.0f} GB/s = {r.get('frac_of_write_peak', 0):.3f} of fill "
