@@ -86,6 +86,8 @@ def parse():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=1,
                     help="launch mode of the headline measurement (1 = the library default: PDL with a full wait)")
+    ap.add_argument("--wide", action="store_true",
+                    help="main region with the high-occupancy build (gymrs_set_launch_occupancy); experiments / ncu captures")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=40)
@@ -355,6 +357,7 @@ def run_b200(args):
         e = make_env(g, env, n, local_rank, (j * world + rank) * n)
         e.set_stream(streams[j % len(streams)].cuda_stream)
         e.set_launch_config(vec=args.vec, block=args.block, pdl=args.pdl)
+        e.set_launch_occupancy(args.wide)
         e.reset(seed=0)
         # ACTION_SETS pre-generated action batches per ring slot, used in rotation, so an env does
         # not see the same action at every step
@@ -450,7 +453,7 @@ def run_b200(args):
     clocks = cs.summary()
     ms = statistics.median(times)
 
-    def one_stream(pdl, pool, reps=3, wide=False):
+    def one_stream(pdl, pool, reps=3, wide=args.wide):
         for e, _ in ring:
             e.set_stream(stream.cuda_stream)
             e.set_launch_config(vec=args.vec, block=args.block, pdl=pdl)
@@ -458,7 +461,7 @@ def run_b200(args):
         run_steps(len(pool), pool)
         t = statistics.median(over_ranks([timed(K, pool) for _ in range(reps)]))
         for e, _ in ring:
-            e.set_launch_occupancy(False)
+            e.set_launch_occupancy(args.wide)
         return t
 
     # Figures on ONE stream (what a caller with a single env group sees):
@@ -639,7 +642,8 @@ def run_b200(args):
             "method": {
                 "launch": "one step kernel per step (gymrs_step semantics, enqueued through gymrs_step_many: one FFI "
                           "crossing per pass over the ring); the independent ring slots alternate over "
-                          f"{len(streams)} CUDA stream(s) so consecutive launches overlap; pdl={args.pdl}",
+                          f"{len(streams)} CUDA stream(s) so consecutive launches overlap; pdl={args.pdl}"
+                          + ("; high-occupancy build (--wide)" if args.wide else ""),
                 "repeats": repeats, "timing": "CUDA events on the main stream (the other streams fork from the start "
                 "event and join before the end event), barrier + device synchronize on both sides of every region, "
                 "median of repeats of the element-wise max over ranks"},

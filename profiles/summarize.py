@@ -7,6 +7,7 @@ profiles/ (CPU only; needs the `ncu` CLI to read .ncu-rep files).
 writes profiles/<round>_launches_<env>.csv        (per-kernel totals of the launch list)
        profiles/<round>_ncu_<env>.json            (key metrics of each --set full capture)
        profiles/<round>_steady_dram_<env>.json    (single-pass dram bytes, --cache-control none)
+       profiles/<round>_ncu_<env>_wide.json       (the same for the high-occupancy build, tools/profile_wide.sh)
        profiles/roofline_traffic.json             (bytes per launch that bench.py reports as `traffic`)
        profiles/kernel_isolated.json              (avg duration, us, of ONE isolated step-kernel launch per env,
                                                    from the launch list: what bench.py reports as `kernel_us_isolated`)
@@ -126,6 +127,10 @@ def main():
                                 "is the steady-state DRAM traffic")
                 json.dump(summ, open(os.path.join(PROF, f"{rnd}_steady_dram_{env}.json"), "w"), indent=1)
                 traffic[env] = summ["dram__bytes_read.sum"] + summ["dram__bytes_write.sum"]
+    for env in ENVS:  # tools/profile_wide.sh: the high-occupancy build of the step kernel
+        rep = os.path.join(OUT, f"prof_wide_{env}.ncu-rep")
+        if os.path.exists(rep):
+            json.dump(raw_page(rep), open(os.path.join(PROF, f"{rnd}_ncu_{env}_wide.json"), "w"), indent=1)
     rep = os.path.join(OUT, "prof_rollout_cartpole.ncu-rep")
     if os.path.exists(rep):
         json.dump(raw_page(rep), open(os.path.join(PROF, f"{rnd}_ncu_rollout_cartpole.json"), "w"), indent=1)
