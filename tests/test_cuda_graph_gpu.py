@@ -49,7 +49,10 @@ def outputs(env):
     ("cartpole", False, None), ("cartpole", True, None), ("mountain_car", True, None), ("pendulum", False, None),
     # opt-in launch schemes are demoted for captured steps: chained launches (pdl = 2) to a grid-wide
     # dependency, the persistent TMA-staged kernel (vec = 8) to step_kernel; one lane per env stays
-    ("cartpole", False, (8, 0, 2)), ("pendulum", True, (1, 64, 2))])
+    ("cartpole", False, (8, 0, 2)), ("pendulum", True, (1, 64, 2)),
+    # the high-occupancy build exists for host-counted steps only: a captured step of such a handle uses
+    # the device-counted default build (4th entry = gymrs_set_launch_occupancy)
+    ("mountain_car", False, (0, 0, 1, True))])
 def test_replayed_graph_equals_eager_steps(torch, g, kind, time_limit, config):
     from gym_rs_b200 import _capi
     n = 200_000
@@ -58,7 +61,8 @@ def test_replayed_graph_equals_eager_steps(torch, g, kind, time_limit, config):
     eager.reset(seed=11)
     env = make(g, kind, n, time_limit=time_limit)
     if config:
-        env.set_launch_config(*config)
+        env.set_launch_config(*config[:3])
+        env.set_launch_occupancy(len(config) > 3 and config[3])
     env.reset(seed=11)
     # three eager steps first: the device counter must pick up where the host count stands
     for k in range(3):

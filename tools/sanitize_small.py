@@ -15,9 +15,11 @@ import gym_rs_b200 as g  # noqa: E402
 n = 8192 + 6  # not a multiple of 4: the last thread takes the scalar out-of-line path
 gen = torch.Generator(device="cuda").manual_seed(0)
 for cls, hi in ((g.CartPoleEnv, 2), (g.MountainCarEnv, 3), (g.PendulumEnv, 0)):
-    for vec, pdl in ((0, 1), (4, 2), (8, 2), (8, 0), (1, 2)):
+    # last entry: the high-occupancy build (gymrs_set_launch_occupancy), plain and chained
+    for vec, pdl, wide in ((0, 1, False), (4, 2, False), (8, 2, False), (8, 0, False), (1, 2, False), (0, 1, True), (4, 2, True)):
         env = cls(num_envs=n, time_limit=(vec == 4))
         env.set_launch_config(vec=vec, block=0, pdl=pdl)
+        env.set_launch_occupancy(wide)
         env.reset(seed=1)
         if hi:
             acts = [torch.randint(0, hi, (n,), generator=gen, device="cuda", dtype=torch.int32) for _ in range(4)]
