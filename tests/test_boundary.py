@@ -123,7 +123,11 @@ def test_bad_arguments_return_codes_not_crashes():
     h = C.c_void_p()
     assert L.gymrs_create(99, 16, 0, 0, None, 0, C.byref(h)) == _capi.ERR_BAD_ARG
     assert L.gymrs_create(_capi.CARTPOLE, 0, 0, 0, None, 0, C.byref(h)) == _capi.ERR_BAD_ARG
+    # a handle holds at most 2^31 env instances (32-bit env indices inside a launch)
+    assert L.gymrs_create(_capi.CARTPOLE, (1 << 31) + 1, 0, 0, None, 0, C.byref(h)) == _capi.ERR_BAD_ARG
     assert L.gymrs_step(None, None, 0) == _capi.ERR_BAD_ARG
+    assert L.gymrs_set_launch_config(None, 0, 0, 1) == _capi.ERR_BAD_ARG
+    assert L.gymrs_set_launch_occupancy(None, 1) == _capi.ERR_BAD_ARG
     assert L.gymrs_sync(None, None) == _capi.ERR_BAD_ARG
     assert L.gymrs_destroy(None) == 0
 
