@@ -101,17 +101,17 @@ struct CartPole {
         // xacc = temp - PML thetaacc cos / M                                         :429
         const T xacc = L::fma(L::neg(L::mul(L::bc(p.pml_over_m), thetaacc)), cs, temp);
         const T tau = L::bc(p.tau);
-        if (!p.semi_implicit) { // Euler: positions use the OLD velocities          :431-436
-            s[0] = L::fma(tau, x_dot, x);
-            s[1] = L::fma(tau, xacc, x_dot);
-            s[2] = L::fma(tau, theta_dot, theta);
-            s[3] = L::fma(tau, thetaacc, theta_dot);
-        } else { //                                                                  :437-441
-            s[1] = L::fma(tau, xacc, x_dot);
-            s[0] = L::fma(tau, s[1], x);
-            s[3] = L::fma(tau, thetaacc, theta_dot);
-            s[2] = L::fma(tau, s[3], theta);
-        }
+        // Euler: positions advance with the OLD velocities (:431-436); semi-implicit ("Other"): with the
+        // NEW ones (:437-441).  The velocities are the same FMA either way, so the integrator only selects
+        // which velocity the position FMA reads: a uniform select instead of two copies of the update
+        // (a branch made ptxas shuffle eight registers per pair to reconverge).
+        const T x_dot_new = L::fma(tau, xacc, x_dot);
+        const T theta_dot_new = L::fma(tau, thetaacc, theta_dot);
+        const bool semi = p.semi_implicit != 0;
+        s[0] = L::fma(tau, semi ? x_dot_new : x_dot, x);
+        s[2] = L::fma(tau, semi ? theta_dot_new : theta_dot, theta);
+        s[1] = x_dot_new;
+        s[3] = theta_dot_new;
     }
 
     // fast path: |theta| <= pi/4 for every env of the lane                          :420-421
