@@ -524,6 +524,38 @@ def test_vec_widths_and_ragged_sizes_are_bit_identical(torch, g, kind):
             assert np.array_equal(a, b)
 
 
+def test_billion_env_batch_indexing(torch, g):
+    """Maximum-size end of the range: one handle with 2^30 + 1027 MountainCar instances (~20 GB, ragged tail).
+    Env indices are 32-bit inside a launch, byte offsets are not: rows are 4 GB apart and slices around the
+    2^29-th / 2^30-th env and the tail must step exactly like the oracle says, reset keyed by global env id."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~20 GB of free device memory")
+    n = (1 << 30) + 1027
+    env = g.MountainCarEnv(num_envs=n, global_env_offset=7)
+    env.reset(seed=5)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    acts = torch.randint(0, 3, (n,), generator=gen, device="cuda", dtype=torch.int32)
+    slices = [slice(0, 4096), slice((1 << 29) - 2048, (1 << 29) + 2048), slice((1 << 30) - 2048, n)]
+    before = [env.state[:, sl].clone() for sl in slices]
+    for sl, b in zip(slices, before):  # the reset stream at these global ids
+        ref = oracle.reset_batch(oracle.MOUNTAIN_CAR, sl.stop - sl.start, seed=5, global_env_offset=7 + sl.start)
+        assert np.abs(b.cpu().numpy() - ref).max() <= 1e-7
+    out = env.step(acts, autoreset=False)
+    env.sync()
+    for sl, b in zip(slices, before):
+        ref = oracle.step_batch(oracle.MOUNTAIN_CAR, b.cpu().numpy(), acts[sl].cpu().numpy())
+        assert_within(out.observation[:, sl].cpu().numpy(), ref["state"], f"envs {sl.start}..{sl.stop}")
+        assert np.all(out.reward[sl].cpu().numpy() == -1.0)
+        assert np.array_equal(out.done[sl].cpu().numpy(), ref["done"])
+    # every env moved by at most max_speed and stayed in the box (a whole-batch property, checked on the device)
+    assert float(out.observation[0].min()) >= -1.2 - 1e-6 and float(out.observation[0].max()) <= 0.6 + 1e-6
+    assert float(out.observation[1].abs().max()) <= 0.07 + 1e-7
+    env.close()
+    del acts, before, out
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("kind", ["cartpole", "mountain_car", "pendulum"])
 @pytest.mark.parametrize("time_limit", [False, True])
 def test_wide_occupancy_build_is_bit_identical(torch, g, kind, time_limit):
