@@ -15,11 +15,12 @@
 //   chunk     persistent: one CTA per SM (or two), every input row of the CTA's env range fetched
 //             into shared memory at the very start with bulk async copies (one mbarrier per
 //             1024-env slice), warps consume slices as they land and store with STG.128
-//   real      gymrs_step (CartPole, auto-reset) through the C ABI
+//   real      gymrs_step (auto-reset) through the C ABI
+// --env mountain_car | pendulum: the plain variants for that env's rows (2 state rows; Pendulum + 3 obs rows)
 //
 // Build (here):  nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/bin/mode_floor \
 //                  tools/mode_floor.cu -Iinclude -Lgym_rs_b200 -lgymrs_b200 -Xlinker -rpath='$ORIGIN/../../gym_rs_b200'
-// Run (GPU box): tools/bin/mode_floor [--iso-only] [--k 2000]
+// Run (GPU box): tools/bin/mode_floor [--env cartpole|mountain_car|pendulum] [--iso-only] [--k 2000]
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -84,6 +85,35 @@ __global__ void __launch_bounds__(128) copy_plain(Slot s, uint32_t n, int prefet
 #pragma unroll
     for (int r = 0; r < 4; ++r) *reinterpret_cast<float4 *>(s.state + (size_t)r * n + i0) = v[r];
     *reinterpret_cast<float4 *>(s.reward + i0) = make_float4(v[0].x, v[1].y, v[2].z, v[3].w);
+    *reinterpret_cast<uchar4 *>(s.done + i0) = make_uchar4(v[0].x > 0, v[0].y > 0, v[0].z > 0, v[0].w > 0);
+}
+
+// the same scheme for any env's rows: SR state rows updated in place, the action row read, OR observation rows
+// written (Pendulum: cos, sin, theta_dot; 0 where the observation IS the state), reward and done written
+template <int SR, int OR>
+__global__ void __launch_bounds__(128) copy_rows(Slot s, float *obs, uint32_t n, int prefetch)
+{
+    extern __shared__ unsigned char pad[];
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (prefetch && threadIdx.x <= SR) {
+        const uint32_t cta0 = blockIdx.x * blockDim.x * 4u;
+        const void *src = threadIdx.x < SR ? (const void *)(s.state + (size_t)threadIdx.x * n + cta0) : (const void *)(s.act + cta0);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(blockDim.x * 16u) : "memory");
+    }
+    pdl_launch_dependents();
+    pdl_wait();
+    if (i0 >= n) return;
+    float4 v[SR];
+#pragma unroll
+    for (int r = 0; r < SR; ++r) v[r] = __ldcg(reinterpret_cast<const float4 *>(s.state + (size_t)r * n + i0));
+    const int4 a = __ldg(reinterpret_cast<const int4 *>(s.act + i0));
+#pragma unroll
+    for (int r = 0; r < SR; ++r) v[r] = touch(v[r], a, r);
+#pragma unroll
+    for (int r = 0; r < SR; ++r) *reinterpret_cast<float4 *>(s.state + (size_t)r * n + i0) = v[r];
+#pragma unroll
+    for (int r = 0; r < OR; ++r) *reinterpret_cast<float4 *>(obs + (size_t)r * n + i0) = touch(v[r % SR], a, r + 1);
+    *reinterpret_cast<float4 *>(s.reward + i0) = make_float4(v[0].x, v[SR - 1].y, v[0].z, v[SR - 1].w);
     *reinterpret_cast<uchar4 *>(s.done + i0) = make_uchar4(v[0].x > 0, v[0].y > 0, v[0].z > 0, v[0].w > 0);
 }
 
@@ -256,12 +286,19 @@ static void launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t 
 int main(int argc, char **argv)
 {
     bool iso_only = false;
+    std::string env_name = "cartpole";
     Harness h;
     for (int i = 1; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--iso-only")) iso_only = true;
+        else if (!std::strcmp(argv[i], "--env") && i + 1 < argc) env_name = argv[++i];
         else if (!std::strcmp(argv[i], "--k") && i + 1 < argc) h.K = std::atoi(argv[++i]);
     }
     const uint32_t n = 1u << 20;
+    const bool cartpole = env_name == "cartpole", pendulum = env_name == "pendulum";
+    if (!cartpole && !pendulum && env_name != "mountain_car") { std::fprintf(stderr, "--env cartpole | mountain_car | pendulum\n"); return 2; }
+    const int kind = cartpole ? GYMRS_CARTPOLE : pendulum ? GYMRS_PENDULUM : GYMRS_MOUNTAIN_CAR;
+    const int state_rows = cartpole ? 4 : 2, obs_rows = pendulum ? 3 : 0;
+    const double mb = (4.0 * (2 * state_rows + obs_rows + 2) + 1) * n / 1e6; // algorithmic bytes per launch
     int sms = 148;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     CK(cudaStreamCreateWithFlags(&h.s0, cudaStreamNonBlocking));
@@ -273,8 +310,10 @@ int main(int argc, char **argv)
 
     // ring of independent batches (larger than L2 together)
     std::vector<Slot> slots(h.ring);
+    std::vector<float *> obs(h.ring, nullptr);
     std::vector<int32_t> host_act(n);
     for (int i = 0; i < h.ring; ++i) {
+        if (obs_rows) { CK(cudaMalloc(&obs[i], 4ull * obs_rows * n)); }
         float *st, *rw;
         int32_t *ac;
         uint8_t *dn;
@@ -284,14 +323,18 @@ int main(int argc, char **argv)
         CK(cudaMalloc(&dn, n));
         CK(cudaMemset(st, 0, 16ull * n));
         uint32_t x = 12345u + i;
-        for (uint32_t j = 0; j < n; ++j) { x = x * 1664525u + 1013904223u; host_act[j] = (x >> 16) & 1; }
+        for (uint32_t j = 0; j < n; ++j) {
+            x = x * 1664525u + 1013904223u;
+            if (pendulum) { const float u = (float)((x >> 8) & 0xffff) / 65536.0f * 4.0f - 2.0f; std::memcpy(&host_act[j], &u, 4); }
+            else host_act[j] = (x >> 16) % (cartpole ? 2 : 3);
+        }
         CK(cudaMemcpy(ac, host_act.data(), 4ull * n, cudaMemcpyHostToDevice));
         slots[i] = Slot{st, ac, rw, dn};
     }
     // the library's handles over their own memory
     std::vector<gymrs_env *> envs(h.ring);
     for (int i = 0; i < h.ring; ++i) {
-        if (gymrs_create(GYMRS_CARTPOLE, n, 0, (uint64_t)i * n, nullptr, 0, &envs[i])) { std::fprintf(stderr, "%s\n", gymrs_last_error()); return 1; }
+        if (gymrs_create(kind, n, 0, (uint64_t)i * n, nullptr, 0, &envs[i])) { std::fprintf(stderr, "%s\n", gymrs_last_error()); return 1; }
         uint64_t seed = 7;
         gymrs_reset(envs[i], &seed, nullptr, nullptr, nullptr, nullptr);
         gymrs_sync(envs[i], nullptr);
@@ -312,16 +355,27 @@ int main(int argc, char **argv)
     struct Variant { std::string name; Launch f; bool is_real; };
     std::vector<Variant> vs;
     vs.push_back({"empty", [&](int, cudaStream_t st) { launch_pdl(empty_kernel, dim3(1), dim3(32), 0, st, true); }, false});
-    vs.push_back({"plain16", [&](int i, cudaStream_t st) { launch_pdl(copy_plain, dim3(grid_plain), dim3(128), 0, st, true, slots[i], n, 1); }, false});
-    vs.push_back({"plain16-nopf", [&](int i, cudaStream_t st) { launch_pdl(copy_plain, dim3(grid_plain), dim3(128), 0, st, true, slots[i], n, 0); }, false});
-    vs.push_back({"plain10", [&](int i, cudaStream_t st) { launch_pdl(copy_plain, dim3(grid_plain), dim3(128), pad10, st, true, slots[i], n, 1); }, false});
-    vs.push_back({"chunk 1x1024", [&](int i, cudaStream_t st) { launch_pdl(copy_chunk<1024>, dim3(sms), dim3(1024), chunk_smem(sl1), st, true, slots[i], n, sl1, 0); }, false});
-    vs.push_back({"chunk 1x768", [&](int i, cudaStream_t st) { launch_pdl(copy_chunk<768>, dim3(sms), dim3(768), chunk_smem(sl1), st, true, slots[i], n, sl1, 0); }, false});
-    vs.push_back({"chunk 2x512", [&](int i, cudaStream_t st) { launch_pdl(copy_chunk<512>, dim3(2 * sms), dim3(512), chunk_smem(sl2), st, true, slots[i], n, sl2, 0); }, false});
+    auto rows = [&](int i, cudaStream_t st, size_t smem, int pf) {
+        if (pendulum) launch_pdl(copy_rows<2, 3>, dim3(grid_plain), dim3(128), smem, st, true, slots[i], obs[i], n, pf);
+        else launch_pdl(copy_rows<2, 0>, dim3(grid_plain), dim3(128), smem, st, true, slots[i], obs[i], n, pf);
+    };
+    if (!cartpole) {
+        CK(cudaFuncSetAttribute(copy_rows<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(copy_rows<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        vs.push_back({"plain16", [&](int i, cudaStream_t st) { rows(i, st, 0, 1); }, false});
+        vs.push_back({"plain16-nopf", [&](int i, cudaStream_t st) { rows(i, st, 0, 0); }, false});
+        vs.push_back({"plain10", [&](int i, cudaStream_t st) { rows(i, st, pad10, 1); }, false});
+    }
+    if (cartpole) vs.push_back({"plain16", [&](int i, cudaStream_t st) { launch_pdl(copy_plain, dim3(grid_plain), dim3(128), 0, st, true, slots[i], n, 1); }, false});
+    if (cartpole) vs.push_back({"plain16-nopf", [&](int i, cudaStream_t st) { launch_pdl(copy_plain, dim3(grid_plain), dim3(128), 0, st, true, slots[i], n, 0); }, false});
+    if (cartpole) vs.push_back({"plain10", [&](int i, cudaStream_t st) { launch_pdl(copy_plain, dim3(grid_plain), dim3(128), pad10, st, true, slots[i], n, 1); }, false});
+    if (cartpole) vs.push_back({"chunk 1x1024", [&](int i, cudaStream_t st) { launch_pdl(copy_chunk<1024>, dim3(sms), dim3(1024), chunk_smem(sl1), st, true, slots[i], n, sl1, 0); }, false});
+    if (cartpole) vs.push_back({"chunk 1x768", [&](int i, cudaStream_t st) { launch_pdl(copy_chunk<768>, dim3(sms), dim3(768), chunk_smem(sl1), st, true, slots[i], n, sl1, 0); }, false});
+    if (cartpole) vs.push_back({"chunk 2x512", [&](int i, cudaStream_t st) { launch_pdl(copy_chunk<512>, dim3(2 * sms), dim3(512), chunk_smem(sl2), st, true, slots[i], n, sl2, 0); }, false});
     vs.push_back({"real step", [&](int i, cudaStream_t) { gymrs_step(envs[i], slots[i].act, GYMRS_STEP_AUTORESET); }, true});
 
-    std::printf("%-14s %10s %12s %12s %10s   (us per 1M-env launch; 43.0 MB algorithmic per launch)\n", "variant", "2 streams",
-                "1 str cold", "1 str L2-res", "isolated");
+    std::printf("%-14s %10s %12s %12s %10s   (%s, us per 1M-env launch; %.1f MB algorithmic per launch)\n", "variant", "2 streams",
+                "1 str cold", "1 str L2-res", "isolated", env_name.c_str(), mb);
     for (auto &v : vs) {
         double a = 0, b = 0, c = 0, d = 0;
         if (v.is_real) bind(h.s0, 1);
