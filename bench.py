@@ -336,9 +336,18 @@ def run_b200(args):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    # Which GPU this rank drives: with fewer ranks than visible GPUs the ranks are spread over the box (GPU
+    # r * visible / N), because neighbouring GPUs share a PCIe root complex and its host-write bandwidth -- that
+    # is the e2e figure's ceiling on a multi-GPU host (gym_rs_b200/sharding.py).  GYMRS_BENCH_SPREAD=0: GPU r.
+    from gym_rs_b200.sharding import device_for_rank
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    visible = torch.cuda.device_count()
+    spread = os.environ.get("GYMRS_BENCH_SPREAD", "1") != "0"
+    dev_index = device_for_rank(local_rank, local_world, visible, spread=spread)
+    dev_stride = visible // local_world if spread else 1
+    torch.cuda.set_device(dev_index)
+    device = torch.device("cuda", dev_index)
+    numa = bind_to_gpu_numa_node(dev_index) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
@@ -354,7 +363,7 @@ def run_b200(args):
     streams = [stream] + [torch.cuda.Stream(device) for _ in range(max(args.streams, 1) - 1)]
     ring = []
     for j in range(args.ring):
-        e = make_env(g, env, n, local_rank, (j * world + rank) * n)
+        e = make_env(g, env, n, dev_index, (j * world + rank) * n)
         e.set_stream(streams[j % len(streams)].cuda_stream)
         e.set_launch_config(vec=args.vec, block=args.block, pdl=args.pdl)
         e.set_launch_occupancy(args.wide)
@@ -448,7 +457,7 @@ def run_b200(args):
     # every repeat costs two barriers, so multi-rank runs are capped lower.  `est` is the max over
     # ranks, so every rank computes the same count (the barriers must pair up).
     repeats = int(min(2000 if world == 1 else 400, max(3, 400.0 / max(est, 1e-3))))
-    with ClockSampler(local_rank) as cs:
+    with ClockSampler(dev_index) as cs:
         times = over_ranks([timed(K, handles) for _ in range(repeats)])
     clocks = cs.summary()
     ms = statistics.median(times)
@@ -644,6 +653,9 @@ def run_b200(args):
                           "crossing per pass over the ring); the independent ring slots alternate over "
                           f"{len(streams)} CUDA stream(s) so consecutive launches overlap; pdl={args.pdl}"
                           + ("; high-occupancy build (--wide)" if args.wide else ""),
+                "devices": f"rank r drives cuda:(r * {dev_stride}) "
+                           f"of {visible} visible GPU(s): with fewer ranks than GPUs the ranks are spread over the box, "
+                           "neighbouring GPUs share a PCIe root complex and its host-write bandwidth (sharding.device_for_rank)",
                 "repeats": repeats, "timing": "CUDA events on the main stream (the other streams fork from the start "
                 "event and join before the end event), barrier + device synchronize on both sides of every region, "
                 "median of repeats of the element-wise max over ranks"},

@@ -3,6 +3,7 @@ cartpole.rs:408-448, mountain_car.rs:408-425), so the step path needs NO collect
 
 * `shard_range` -- contiguous global env-id range of a rank; reset sampling is keyed by the global
   id, so per-env results do not depend on the number of shards.
+* `device_for_rank` -- which GPU of the box a rank drives (ranks are spread over the box's PCIe root complexes).
 * `make_sharded_env` -- one handle per process/GPU holding this rank's range.
 * `gather_observations` -- the only (optional) collective: an NCCL all-gather of the observation
   rows for callers that want one contiguous [obs_dim, total_envs] view on every rank
@@ -20,6 +21,21 @@ def shard_range(rank: int, world_size: int, total_envs: int) -> Tuple[int, int]:
     base, extra = divmod(total_envs, world_size)
     begin = rank * base + min(rank, extra)
     return begin, begin + base + (1 if rank < extra else 0)
+
+
+def device_for_rank(local_rank: int, local_world_size: int, visible_devices: int, spread: bool = True) -> int:
+    """CUDA device ordinal of a rank on one box.  With fewer ranks than visible GPUs the ranks are spread over
+    the whole box (rank r -> GPU r * (visible // ranks)) instead of packed onto GPUs 0..ranks-1: the step path
+    itself does not care, but host delivery does -- neighbouring GPUs usually hang off the same PCIe root complex
+    / socket and share its device-to-host write bandwidth (measured on an 8 x B200 host, plain pinned-memory
+    copies: GPUs {0, 1} 72 GB/s, {0, 4} 96 GB/s; {0, 1, 2, 3} 76 GB/s, {0, 2, 4, 6} 114 GB/s;
+    tools/pcie_probe_multi.py).  `spread=False`, or as many ranks as GPUs, gives the identity mapping."""
+    if not (0 <= local_rank < local_world_size) or visible_devices < 1:
+        raise ValueError("bad local_rank / local_world_size / visible_devices")
+    if local_world_size > visible_devices:
+        raise ValueError("more ranks than visible GPUs")
+    stride = visible_devices // local_world_size if spread else 1
+    return local_rank * stride
 
 
 def make_sharded_env(env_cls, total_envs: int, rank: int, world_size: int, device: int, **kw):

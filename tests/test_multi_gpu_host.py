@@ -8,6 +8,7 @@ import sys
 import textwrap
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -94,3 +95,23 @@ def test_shard_range_partitions_exactly():
         sizes = [e - b for b, e in ranges]
         assert max(sizes) - min(sizes) <= 1
     assert shard_range(3, 8, 1 << 23) == (3 << 20, 4 << 20)   # BASELINE config 5: 1M envs per GPU
+
+
+def test_device_for_rank_spreads_ranks_over_the_box():
+    from gym_rs_b200.sharding import device_for_rank
+    # as many ranks as GPUs, or one visible GPU per rank (CUDA_VISIBLE_DEVICES): the identity
+    assert [device_for_rank(r, 8, 8) for r in range(8)] == list(range(8))
+    assert [device_for_rank(r, 2, 2) for r in range(2)] == [0, 1]
+    # fewer ranks than GPUs: spread over the box (different PCIe root complexes), never two ranks on one GPU
+    assert [device_for_rank(r, 2, 8) for r in range(2)] == [0, 4]
+    assert [device_for_rank(r, 4, 8) for r in range(4)] == [0, 2, 4, 6]
+    assert device_for_rank(0, 1, 8) == 0
+    assert [device_for_rank(r, 3, 8) for r in range(3)] == [0, 2, 4]
+    assert [device_for_rank(r, 2, 8, spread=False) for r in range(2)] == [0, 1]
+    for world, visible in ((1, 1), (2, 3), (3, 8), (5, 8), (8, 8)):
+        devs = [device_for_rank(r, world, visible) for r in range(world)]
+        assert len(set(devs)) == world and max(devs) < visible
+    with pytest.raises(ValueError):
+        device_for_rank(0, 4, 2)
+    with pytest.raises(ValueError):
+        device_for_rank(2, 2, 8)
