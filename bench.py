@@ -380,9 +380,13 @@ def run_b200(args):
     step_many = L.gymrs_step_many
     _arrays = {}
 
-    def run_steps(k, pool):
+    step_pass = L.gymrs_step_pass
+
+    def run_steps(k, pool, begin_event=None):
         """k consecutive steps over the pool's (handle, action batch) pairs in order: gymrs_step_many, i.e.
-        one gymrs_step per pair with one FFI crossing per pass over the pool (no Python between launches)."""
+        one gymrs_step per pair with one FFI crossing per pass over the pool (no Python between launches).
+        begin_event (a raw cudaEvent_t): gymrs_step_pass records it on the first handle's stream and forks the
+        other streams of the pass from it inside the same call, so that nothing but the launches follows it."""
         m = len(pool)
         if id(pool) not in _arrays:
             _arrays[id(pool)] = ((C.c_void_p * m)(*[h.value if hasattr(h, "value") else h for h, _ in pool]),
@@ -391,7 +395,11 @@ def run_b200(args):
         left = k
         while left > 0:
             c = min(m, left)
-            rc = step_many(hs, acts, c, AR, None)
+            if begin_event is not None:
+                rc = step_pass(hs, acts, c, AR, begin_event, None, None)
+                begin_event = None
+            else:
+                rc = step_many(hs, acts, c, AR, None)
             if rc:
                 _capi.check(rc)
             left -= c
@@ -401,11 +409,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    def fork(ev):  # extra streams (if any) start after ev ...
-        for s in streams[1:]:
-            s.wait_event(ev)
-
-    def join():    # ... and the main stream's end event waits for all of them
+    def join():    # the main stream's end event waits for the extra streams (they fork inside gymrs_step_pass)
         for s in streams[1:]:
             e_ = torch.cuda.Event()
             e_.record(s)
@@ -425,11 +429,14 @@ def run_b200(args):
         once at the end, on the whole vector of repeats.  The host clock runs from the first launch
         to the drained device and excludes the barriers; it is only recorded (timing_sanity)."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)  # creates the CUDA event; the record that counts is the one gymrs_step_pass makes below
+        begin = C.c_void_p(ev0.cuda_event)
         barrier()
         w0 = time.perf_counter()
-        ev0.record(stream)
-        fork(ev0)
-        run_steps(k, pool)
+        # start event + fork of the other streams + the launches in ONE library call: the first pass of the pool
+        # covers every ring slot, hence every stream (Python between the start event and the first launch would
+        # be ~10 us of idle device inside a 130 us region)
+        run_steps(k, pool, begin_event=begin)
         join()
         ev1.record(stream)
         torch.cuda.synchronize(device)
@@ -657,7 +664,7 @@ def run_b200(args):
                            f"of {visible} visible GPU(s): with fewer ranks than GPUs the ranks are spread over the box, "
                            "neighbouring GPUs share a PCIe root complex and its host-write bandwidth (sharding.device_for_rank)",
                 "repeats": repeats, "timing": "CUDA events on the main stream (the other streams fork from the start "
-                "event and join before the end event), barrier + device synchronize on both sides of every region, "
+                "event -- recorded, together with the fork and the launches, by one gymrs_step_pass call -- and join before the end event), barrier + device synchronize on both sides of every region, "
                 "median of repeats of the element-wise max over ranks"},
             "timing_sanity": {"regions": sanity["regions"], "device_ms_total": sanity["device_ms"],
                               "host_ms_total": sanity["host_ms"],

@@ -100,6 +100,7 @@ SIGNATURES = {
     "gymrs_sync": (_i, [_vp, _pu64]),
     "gymrs_set_launch_config": (_i, [_vp, _i, _i, _i]),
     "gymrs_set_launch_occupancy": (_i, [_vp, _i]),
+    "gymrs_step_pass": (_i, [C.POINTER(_vp), C.POINTER(_vp), _u32, _u32, _vp, _vp, C.POINTER(_u32)]),
     "gymrs_host_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "gymrs_host_free": (_i, [_vp]),
     "gymrs_clip": (C.c_double, [C.c_double, C.c_double, C.c_double]),

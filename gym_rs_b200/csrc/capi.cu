@@ -154,6 +154,7 @@ struct gymrs_env {
     bool device_counted = false;
     uint64_t generation = 0; // see BatchArgs::generation
     cudaEvent_t switch_ev = nullptr; // orders a new stream after the old one (gymrs_set_stream)
+    cudaEvent_t join_ev = nullptr;   // joins this handle's stream into the first handle's (gymrs_step_pass), created on first use
     bool sbt_dirty = false;  // some env may hold steps_beyond_terminated = Some(_)
     int vec = 0, block = 0, pdl = 1;
     bool wide = false;              // gymrs_set_launch_occupancy
@@ -465,6 +466,7 @@ int free_env(gymrs_env *e)
     for (auto &s : e->copy_streams) if (s) cudaStreamDestroy(s);
     for (auto &v : e->hev) if (v) cudaEventDestroy(v);
     if (e->switch_ev) cudaEventDestroy(e->switch_ev);
+    if (e->join_ev) cudaEventDestroy(e->join_ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return GYMRS_OK;
@@ -844,6 +846,51 @@ int gymrs_step_many(gymrs_env *const *envs, const void *const *actions, uint32_t
         if (done) *done = i + 1;
     }
     return GYMRS_OK;
+}
+
+// A pass over several handles bracketed by two caller-owned events: `begin` is recorded on the first
+// handle's stream before anything is launched and every other stream of the pass waits for it, `end`
+// is recorded on the first handle's stream once every other stream of the pass has been joined into
+// it.  All in one FFI crossing, so nothing but the launches themselves sits between the two events.
+int gymrs_step_pass(gymrs_env *const *envs, const void *const *actions, uint32_t count, uint32_t step_flags,
+                    void *begin_event, void *end_event, uint32_t *done)
+{
+    if (done) *done = 0;
+    if (count && (!envs || !actions)) return fail(GYMRS_ERR_BAD_ARG, "NULL argument");
+    if (!begin_event && !end_event) return gymrs_step_many(envs, actions, count, step_flags, done);
+    if (count == 0) return fail(GYMRS_ERR_BAD_ARG, "a pass with events needs at least one step");
+    for (uint32_t i = 0; i < count; ++i) {
+        if (!envs[i]) return fail(GYMRS_ERR_BAD_ARG, "NULL handle");
+        if (envs[i]->device != envs[0]->device) return fail(GYMRS_ERR_BAD_ARG, "the handles of a pass with events must share a device");
+    }
+    gymrs_env *first = envs[0];
+    if (int rc_ = refuse_in_capture(first, "gymrs_step_pass with events")) return rc_;
+    ON_DEVICE(first->device);
+    // the other streams of the pass, each with the first handle that uses it
+    std::vector<gymrs_env *> others;
+    for (uint32_t i = 1; i < count; ++i) {
+        bool seen = envs[i]->stream == first->stream;
+        for (gymrs_env *o : others) seen = seen || o->stream == envs[i]->stream;
+        if (!seen) others.push_back(envs[i]);
+    }
+    if (begin_event) {
+        CU(cudaEventRecord((cudaEvent_t)begin_event, first->stream));
+        for (gymrs_env *o : others) CU(cudaStreamWaitEvent(o->stream, (cudaEvent_t)begin_event, 0));
+    }
+    int rc = GYMRS_OK;
+    for (uint32_t i = 0; i < count && rc == GYMRS_OK; ++i) {
+        rc = gymrs_step(envs[i], actions[i], step_flags);
+        if (rc == GYMRS_OK && done) *done = i + 1;
+    }
+    if (end_event) { // also after a failed launch: what was enqueued is still bracketed
+        for (gymrs_env *o : others) {
+            if (!o->join_ev) CU(cudaEventCreateWithFlags(&o->join_ev, cudaEventDisableTiming));
+            CU(cudaEventRecord(o->join_ev, o->stream));
+            CU(cudaStreamWaitEvent(first->stream, o->join_ev, 0));
+        }
+        CU(cudaEventRecord((cudaEvent_t)end_event, first->stream));
+    }
+    return rc;
 }
 
 } // extern "C"

@@ -157,6 +157,16 @@ int gymrs_step(gymrs_env *env, const void *actions, uint32_t step_flags);
 int gymrs_step_many(gymrs_env *const *envs, const void *const *actions, uint32_t count, uint32_t step_flags,
                     uint32_t *done);
 
+/* gymrs_step_many bracketed by two caller-owned CUDA events (cudaEvent_t, either may be NULL): `begin_event` is
+ * recorded on the first handle's stream before anything is launched and every other stream of the pass waits for
+ * it; `end_event` is recorded on the first handle's stream after every other stream of the pass has been joined
+ * into it -- ONE event that completes when the whole pass has (what a consumer on another stream waits for, or,
+ * with timing enabled, what a pass took on the device with nothing but its launches between the two records).
+ * The handles must share a device; not inside a stream capture.  The reference's counterpart is the caller's
+ * loop over its env objects (examples/cartpole.rs:15-30), which needs no such thing on one CPU thread. */
+int gymrs_step_pass(gymrs_env *const *envs, const void *const *actions, uint32_t count, uint32_t step_flags,
+                    void *begin_event, void *end_event, uint32_t *done);
+
 /* Same step with HOST buffers: copies actions in, steps, copies observation / reward / done
  * out (any output pointer may be NULL to skip it) and synchronises.  obs: [obs_dim][num_envs]. */
 int gymrs_step_host(gymrs_env *env, const void *actions, uint32_t step_flags,

@@ -130,6 +130,8 @@ extern "C" {
     pub fn gymrs_step(env: *mut gymrs_env, actions: *const c_void, step_flags: u32) -> c_int;
     pub fn gymrs_step_many(envs: *const *mut gymrs_env, actions: *const *const c_void, count: u32, step_flags: u32,
                            done: *mut u32) -> c_int;
+    pub fn gymrs_step_pass(envs: *const *mut gymrs_env, actions: *const *const c_void, count: u32, step_flags: u32,
+                           begin_event: *mut c_void, end_event: *mut c_void, done: *mut u32) -> c_int;
     pub fn gymrs_step_host(env: *mut gymrs_env, actions: *const c_void, step_flags: u32, obs: *mut f32,
                            reward: *mut f32, done: *mut u8, truncated: *mut u8) -> c_int;
     pub fn gymrs_step_host_async(env: *mut gymrs_env, actions: *const c_void, step_flags: u32, obs: *mut f32,

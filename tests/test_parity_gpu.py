@@ -524,6 +524,50 @@ def test_vec_widths_and_ragged_sizes_are_bit_identical(torch, g, kind):
             assert np.array_equal(a, b)
 
 
+def test_step_pass_brackets_a_multi_stream_pass_with_events(torch, g):
+    """gymrs_step_pass = gymrs_step_many + a begin event (recorded on the first handle's stream, the other streams
+    of the pass fork from it) + an end event (recorded there after the other streams have been joined)."""
+    import ctypes as C
+    from gym_rs_b200 import _capi
+    L = _capi.load()
+    n = 1 << 18
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    envs = [g.CartPoleEnv(num_envs=n, global_env_offset=i * n) for i in range(4)]
+    refs = [g.CartPoleEnv(num_envs=n, global_env_offset=i * n) for i in range(4)]
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    acts = [torch.randint(0, 2, (n,), generator=gen, device="cuda", dtype=torch.int32) for _ in range(4)]
+    for i, (e, r) in enumerate(zip(envs, refs)):
+        e.reset(seed=9)
+        r.reset(seed=9)
+        e.sync()
+        e.set_stream((s1 if i % 2 == 0 else s2).cuda_stream)
+    torch.cuda.synchronize()
+    b, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b.record(s1)
+    e_.record(s1)  # creates the CUDA events
+    torch.cuda.synchronize()
+    order = [0, 1, 2, 3, 0, 1, 2, 3]
+    hs = (C.c_void_p * len(order))(*[envs[i].handle.value if hasattr(envs[i].handle, "value") else envs[i].handle for i in order])
+    ap = (C.c_void_p * len(order))(*[acts[(k + i) % 4].data_ptr() for k, i in enumerate(order)])
+    done = C.c_uint32(0)
+    _capi.check(L.gymrs_step_pass(hs, ap, len(order), _capi.STEP_AUTORESET, C.c_void_p(b.cuda_event), C.c_void_p(e_.cuda_event),
+                                  C.byref(done)))
+    assert done.value == len(order)
+    e_.synchronize()  # ONE event covers both streams
+    assert b.elapsed_time(e_) > 0
+    for k, i in enumerate(order):
+        refs[i].step(acts[(k + i) % 4], autoreset=True)
+    for e, r in zip(envs, refs):
+        r.sync()
+        # no sync on e: the end event alone must have made both streams' results visible
+        assert torch.equal(e._t_state, r._t_state) and torch.equal(e._t_done, r._t_done)
+    # without events it is gymrs_step_many; an empty pass with events is refused
+    _capi.check(L.gymrs_step_pass(hs, ap, 2, _capi.STEP_AUTORESET, None, None, None))
+    assert L.gymrs_step_pass(hs, ap, 0, _capi.STEP_AUTORESET, C.c_void_p(b.cuda_event), None, None) == _capi.ERR_BAD_ARG
+    for x in envs + refs:
+        x.close()
+
+
 def test_billion_env_batch_indexing(torch, g):
     """Maximum-size end of the range: one handle with 2^30 + 1027 MountainCar instances (~20 GB, ragged tail).
     Env indices are 32-bit inside a launch, byte offsets are not: rows are 4 GB apart and slices around the
