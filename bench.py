@@ -340,8 +340,8 @@ def run_b200(args):
     # r * visible / N), because neighbouring GPUs share a PCIe root complex and its host-write bandwidth -- that
     # is the e2e figure's ceiling on a multi-GPU host (gym_rs_b200/sharding.py).  GYMRS_BENCH_SPREAD=0: GPU r.
     from gym_rs_b200.sharding import device_for_rank
-    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
     visible = torch.cuda.device_count()
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", min(world, visible)))
     spread = os.environ.get("GYMRS_BENCH_SPREAD", "1") != "0"
     dev_index = device_for_rank(local_rank, local_world, visible, spread=spread)
     dev_stride = visible // local_world if spread else 1
