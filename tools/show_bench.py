@@ -1,5 +1,10 @@
+"""One-line summary of a bench.py JSON line piped in on stdin (used by the sweep scripts):
+    python bench.py ... | python tools/show_bench.py <tag>
+For files use tools/bench_summary.py; with a terminal on stdin this refuses instead of waiting forever."""
 import json,sys
 tag=sys.argv[1]
+if sys.stdin.isatty():
+    sys.exit("show_bench.py reads a bench.py line from stdin; for files use tools/bench_summary.py")
 try:
     d=json.loads([l for l in sys.stdin.read().splitlines() if l.startswith('{')][-1])
     r=d.get("rollout") or {}
