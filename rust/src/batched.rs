@@ -117,6 +117,16 @@ impl BatchedEnv {
         ffi::check(ffi::gymrs_step(self.handle, actions_dev, flags));
     }
 
+    /// Launch tuning (no counterpart in the reference): `pdl` 0 / 1 / 2 and the step kernel's occupancy, see
+    /// `gymrs_set_launch_config` / `gymrs_set_launch_occupancy` in `include/gymrs_b200.h`.  `wide` suits several
+    /// handles stepped round-robin on one stream; the defaults suit everything else.
+    pub fn set_launch_tuning(&mut self, pdl: i32, wide: bool) {
+        unsafe {
+            ffi::check(ffi::gymrs_set_launch_config(self.handle, 0, 0, pdl));
+            ffi::check(ffi::gymrs_set_launch_occupancy(self.handle, if wide { 1 } else { 0 }));
+        }
+    }
+
     /// Device pointers to the handle's SoA arrays (observation, reward, done, truncated, ...).
     pub fn buffers(&self) -> ffi::gymrs_buffers {
         let mut b = std::mem::MaybeUninit::<ffi::gymrs_buffers>::zeroed();
