@@ -873,12 +873,20 @@ int gymrs_step_pass(gymrs_env *const *envs, const void *const *actions, uint32_t
         for (gymrs_env *o : others) seen = seen || o->stream == envs[i]->stream;
         if (!seen) others.push_back(envs[i]);
     }
-    if (begin_event) {
-        CU(cudaEventRecord((cudaEvent_t)begin_event, first->stream));
-        for (gymrs_env *o : others) CU(cudaStreamWaitEvent(o->stream, (cudaEvent_t)begin_event, 0));
-    }
+    if (begin_event) CU(cudaEventRecord((cudaEvent_t)begin_event, first->stream));
+    // each other stream is forked from the begin event right before its first launch of the pass, so that
+    // the first launch follows the begin record with nothing in between
+    std::vector<cudaStream_t> forked;
     int rc = GYMRS_OK;
     for (uint32_t i = 0; i < count && rc == GYMRS_OK; ++i) {
+        if (begin_event && envs[i]->stream != first->stream) {
+            bool is_forked = false;
+            for (cudaStream_t s : forked) is_forked = is_forked || s == envs[i]->stream;
+            if (!is_forked) {
+                CU(cudaStreamWaitEvent(envs[i]->stream, (cudaEvent_t)begin_event, 0));
+                forked.push_back(envs[i]->stream);
+            }
+        }
         rc = gymrs_step(envs[i], actions[i], step_flags);
         if (rc == GYMRS_OK && done) *done = i + 1;
     }
