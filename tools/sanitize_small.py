@@ -57,6 +57,28 @@ for cls, hi in ((g.CartPoleEnv, 2), (g.MountainCarEnv, 3), (g.PendulumEnv, 0)):
             env.rollout_host(torch.stack(h).pin_memory(), hobs, hrew, hdone, None, n_steps=5)
         env.sync()
         env.close()
+# gymrs_step_pass: a two-stream pass bracketed by events
+import ctypes as C  # noqa: E402
+from gym_rs_b200 import _capi  # noqa: E402
+_L = _capi.load()
+_s1, _s2 = torch.cuda.Stream(), torch.cuda.Stream()
+_envs = [g.MountainCarEnv(num_envs=n, global_env_offset=i * n) for i in range(2)]
+for _i, _e in enumerate(_envs):
+    _e.reset(seed=2)
+    _e.sync()
+    _e.set_stream((_s1 if _i == 0 else _s2).cuda_stream)
+_a = torch.randint(0, 3, (n,), generator=gen, device="cuda", dtype=torch.int32)
+_b, _d = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+_b.record(_s1)
+_d.record(_s1)
+torch.cuda.synchronize()
+_hs = (C.c_void_p * 4)(*[_envs[i % 2].handle.value for i in range(4)])
+_ap = (C.c_void_p * 4)(*[_a.data_ptr()] * 4)
+_capi.check(_L.gymrs_step_pass(_hs, _ap, 4, _capi.STEP_AUTORESET, C.c_void_p(_b.cuda_event), C.c_void_p(_d.cuda_event), None))
+_d.synchronize()
+for _e in _envs:
+    _e.sync()
+    _e.close()
 # device-counted kernel variants (CUDA-graph capture): captured steps + rollout + seeded reset,
 # replayed, then an eager step, a host step, a checkpoint round trip and a clone on the same handle
 side = torch.cuda.Stream()
